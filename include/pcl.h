@@ -1,0 +1,166 @@
+/*
+ * pcl.h -- C ABI of libpcl_b200.so: the point-cloud reconstruction-loss hot path
+ * (Chamfer distance and auction EMD, forward + backward) for NVIDIA B200 (sm_100a).
+ *
+ * This is the drop-in boundary for the native layer the reference reaches through
+ *   - the pybind11 module `emd` (pointcloud_vision/loss/emd/emd.cpp:28-31: forward/backward,
+ *     implemented in loss/emd/emd_cuda.cu:228-316) and
+ *   - pytorch3d's `_C.knn_points_idx` / `_C.knn_points_backward` under
+ *     `pytorch3d.loss.chamfer_distance` (call sites pointcloud_vision/utils.py:211,228).
+ *
+ * Conventions
+ *   - every pointer is a DEVICE pointer owned by the caller unless its name ends in `_host`;
+ *     the library never allocates or frees device memory (reference: caller-allocates,
+ *     emd_module.py:45-56) -- scratch is one opaque workspace sized by *_workspace_bytes();
+ *   - point arrays are (B, P, D) with element strides (batch_stride, row_stride) and unit
+ *     channel stride, so strided views such as pred[:, :, :3] (utils.py:254) need no copy;
+ *     `dtype` selects the element type of such an input: PCL_F32, PCL_F16 or PCL_BF16 (the
+ *     kernels up-cast exactly like `.float()`, emd_module.py:43-44); outputs are fp32 / int32;
+ *   - all calls are asynchronous on `stream` (a cudaStream_t passed as void*; NULL = legacy
+ *     default stream, which is what the reference uses, emd_cuda.cu:257-269);
+ *   - return value: 0 = ok, negative = error (PCL_E_*), text via pcl_last_error() (thread-local).
+ *     The reference printf()s and returns -1/0/1 (emd_cuda.cu:236-249,276-281); no printf here.
+ *   - there is no CPU fallback: without a CUDA device every compute entry point fails.
+ */
+#ifndef PCL_B200_H
+#define PCL_B200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define PCL_VERSION 100 /* major*100 + minor */
+
+#if defined(__GNUC__)
+#define PCL_API __attribute__((visibility("default")))
+#else
+#define PCL_API
+#endif
+
+enum { PCL_F32 = 0, PCL_F16 = 1, PCL_BF16 = 2 };
+
+enum {
+    PCL_OK = 0,
+    PCL_E_SHAPE = -1,     /* bad sizes (reference: emd_cuda.cu:236-249 returns -1) */
+    PCL_E_ARG = -2,       /* null pointer / bad enum */
+    PCL_E_CUDA = -3,      /* a CUDA call or launch failed (reference returns 0, emd_cuda.cu:276-281) */
+    PCL_E_WORKSPACE = -4, /* workspace too small */
+    PCL_E_UNSUPPORTED = -5
+};
+
+/* Chamfer arithmetic: how one squared distance is rounded (see DESIGN.md "Chamfer arithmetic"). */
+enum {
+    PCL_CHAMFER_UNFUSED = 0, /* ((dx*dx)+dy*dy)+dz*dz -- pytorch3d CPU build; the default */
+    PCL_CHAMFER_FMA = 1      /* fma(dz,dz,fma(dy,dy,dx*dx)) -- what nvcc makes of pytorch3d's knn.cu */
+};
+
+PCL_API int pcl_version(void);
+PCL_API const char *pcl_last_error(void);
+/* Number of SMs / compute capability of the current device, for sizing and for the bench roofline. */
+PCL_API int pcl_device_info(int *sm_count, int *cc_major, int *cc_minor, int *max_smem_optin);
+
+/* ------------------------------------------------------------------ Chamfer ------------------------------- */
+/*
+ * Replaces pytorch3d.loss.chamfer_distance(x, y, x_lengths, y_lengths)[0] forward
+ * (utils.py:211,228): two directed K=1 nearest-neighbour searches with squared L2, lowest index
+ * on exact ties, padded rows ignored, then point mean and batch mean.
+ *   x (B,P1,D), y (B,P2,D); x_len / y_len: nullable int64[B] (entries in [0,P]); 1 <= D <= 8.
+ *   dist_x,idx_x: (B,P1)  dist_y,idx_y: (B,P2)   (padded rows: 0 / 0)
+ *   loss_xy[2] = { sum_n mean_i dist_x / max(B,1), same for y }   (loss = loss_xy[0]+loss_xy[1])
+ */
+PCL_API size_t pcl_chamfer_workspace_bytes(int B, int P1, int P2);
+PCL_API int pcl_chamfer_fwd(const void *x, int x_dtype, int64_t x_bs, int64_t x_rs, const int64_t *x_len,
+                    const void *y, int y_dtype, int64_t y_bs, int64_t y_rs, const int64_t *y_len,
+                    int B, int P1, int P2, int D, int mode,
+                    float *dist_x, int32_t *idx_x, float *dist_y, int32_t *idx_y, float *loss_xy,
+                    void *workspace, size_t workspace_bytes, void *stream);
+/*
+ * Replaces pytorch3d's knn_points_backward applied to both directions plus the mean reductions:
+ *   gdx = g[0] / max(B,1) / clamp(x_len,1);  grad_x[i] += 2*gdx*(x_i - y[idx_x[i]]);  grad_y[idx_x[i]] -= same
+ *   and symmetrically for the y direction with g[1].  `grad_out` is a DEVICE float[2]: the upstream
+ * gradients of loss_xy[0] and loss_xy[1] (no host sync).  grad_x (B,P1,D), grad_y (B,P2,D) are dense
+ * fp32 and are overwritten.
+ */
+PCL_API int pcl_chamfer_bwd(const void *x, int x_dtype, int64_t x_bs, int64_t x_rs, const int64_t *x_len,
+                    const void *y, int y_dtype, int64_t y_bs, int64_t y_rs, const int64_t *y_len,
+                    int B, int P1, int P2, int D, const int32_t *idx_x, const int32_t *idx_y,
+                    const float *grad_out, float *grad_x, float *grad_y, void *stream);
+
+/* ------------------------------------------------------------------ EMD (auction) ------------------------- */
+/*
+ * Replaces emd.forward (emd.cpp:14-18 -> emd_cuda_forward, emd_cuda.cu:228-282): `iters` rounds of
+ * {list unassigned, Bid, GetMax, Assign} then CalcDist, all inside ONE persistent kernel.
+ *   xyz1 = prediction (B,N,3) (receives the gradient), xyz2 = target (B,N,3), both in [0,1]^3.
+ *   dist (B,N) fp32 = squared distance to the matched target, assignment (B,N) int32.
+ *   stats: nullable int32[B*4] = { sum_t U_t, iterations run, GetMax multi-bidder events, cluster size }.
+ * Constraints: 1 <= N <= pcl_emd_max_points(), B >= 0 (the reference needs N%1024==0 and B<=512,
+ * emd_cuda.cu:241-249; both are accepted here, neither is required).
+ * The GetMax race of the reference (emd_cuda.cu:188-191) is resolved deterministically: the
+ * largest bidder index inside the +-1e-6 window wins.
+ */
+PCL_API int pcl_emd_max_points(void);
+PCL_API size_t pcl_emd_workspace_bytes(int B, int N);
+PCL_API int pcl_emd_fwd(const void *xyz1, int dtype1, int64_t bs1, int64_t rs1,
+                const void *xyz2, int dtype2, int64_t bs2, int64_t rs2,
+                int B, int N, float eps, int iters,
+                float *dist, int32_t *assignment, int32_t *stats,
+                void *workspace, size_t workspace_bytes, void *stream);
+/*
+ * Replaces emd.backward (emd.cpp:20-23 -> NmDistanceGradKernel, emd_cuda.cu:284-316):
+ *   grad_xyz1[j] = (2*graddist[j]) * (xyz1[j] - xyz2[assignment[j]]);  the target gets no gradient
+ *   (emd_module.py:69,72).  grad_xyz1 (B,N,3) dense fp32, overwritten (no zero-fill needed).
+ */
+PCL_API int pcl_emd_bwd(const void *xyz1, int dtype1, int64_t bs1, int64_t rs1,
+                const void *xyz2, int dtype2, int64_t bs2, int64_t rs2,
+                int B, int N, const int32_t *assignment, const float *graddist,
+                float *grad_xyz1, void *stream);
+
+/*
+ * Loss epilogue of EarthMoverDistance (utils.py:257-304), fused.
+ * pcl_emd_match_hist: hist[c] += #{(b,j): label(target[b, assignment[b,j]]) == c}  (utils.py:271-275;
+ *   the histogram of the PERMUTED target).  target_label: the channel holding the class id as a float
+ *   (target[..., 3]) given as pointer + strides; hist: int64[C], zeroed by the callee.
+ *   matched_label (nullable, B*N int32) receives the permuted labels for the cross-entropy term.
+ * pcl_emd_weighted_reduce: sums[0] = sum w*sqrt(dist), sums[1] = sum w, with
+ *   w = class_weights[matched_label] (or 1 when class_weights == NULL)  (utils.py:292,304).
+ */
+PCL_API int pcl_emd_match_hist(const void *target_label, int dtype, int64_t bs, int64_t rs,
+                       const int32_t *assignment, int B, int N, int C,
+                       int64_t *hist, int32_t *matched_label, void *stream);
+PCL_API int pcl_emd_weighted_reduce(const float *dist, const int32_t *matched_label, const float *class_weights,
+                            int B, int N, int C, float *sums,
+                            void *workspace /* >= pcl_emd_workspace_bytes(B,N) */, size_t workspace_bytes, void *stream);
+/*
+ * Backward of point_l = sums[0]/sums[1] through sqrt and the auction distance, fused with pcl_emd_bwd:
+ *   graddist = g * w / (2*sqrt(dist)) / sums[1]   =>   grad_xyz1 = 2*graddist*(xyz1 - xyz2[assignment]).
+ * dist == 0 gives inf/nan exactly like the reference's dists.sqrt() (utils.py:304).
+ */
+PCL_API int pcl_emd_weighted_bwd(const void *xyz1, int dtype1, int64_t bs1, int64_t rs1,
+                         const void *xyz2, int dtype2, int64_t bs2, int64_t rs2,
+                         int B, int N, const int32_t *assignment, const float *dist,
+                         const int32_t *matched_label, const float *class_weights, int C,
+                         const float *sums, const float *grad_out, float *grad_xyz1, void *stream);
+
+/* ------------------------------------------------------------------ host-buffer entry points -------------- */
+/*
+ * End-to-end calls with HOST buffers (what a non-torch caller binds; also bench.py's e2e leg).
+ * Inputs are dense fp32 host arrays (pinned memory recommended), outputs are host arrays; the
+ * device staging buffer `dev_scratch` (>= *_host_scratch_bytes) is caller-allocated device memory.
+ * The calls enqueue H2D copies, kernels and D2H copies on `stream` and return without
+ * synchronising; the caller synchronises the stream before reading the outputs.
+ */
+PCL_API size_t pcl_loss_host_scratch_bytes(int B, int N);
+PCL_API int pcl_chamfer_emd_step_host(const float *pred_host, const float *target_host, int B, int N,
+                              float eps, int iters, int chamfer_mode,
+                              float *loss_host /* 3: chamfer loss_x, chamfer loss_y, EMD mean sqrt(dist) */,
+                              float *grad_pred_chamfer_host /* nullable B*N*3 */,
+                              float *grad_pred_emd_host /* nullable B*N*3 */,
+                              void *dev_scratch, size_t dev_scratch_bytes, void *stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* PCL_B200_H */

@@ -1,0 +1,19 @@
+"""pointcloud_b200 -- the point-cloud reconstruction-loss hot path of JoongWonSeo/pointcloud
+(Chamfer distance and auction EMD, forward + backward) re-built for NVIDIA B200 (sm_100a).
+
+Python host layer (this package) mirrors the reference's loss interface
+(pointcloud_vision/utils.py:207-309, pointcloud_vision/loss/emd/emd_module.py); all arithmetic runs in
+hand-written CUDA kernels behind the C ABI of include/pcl.h (libpcl_b200.so).  No CPU fallback.
+"""
+from . import cfg
+from .chamfer import chamfer_distance, chamfer_forward_raw
+from .emd_module import emdFunction, emdModule, emd_forward_raw
+from .losses import (ChamferDistance, EarthMoverDistance, FilterClasses, FilteringChamferDistance,
+                     SegmentingChamferDistance, StatePredictionLoss)
+from .sharded import ShardedLoss, shard_bounds
+
+__all__ = [
+    "cfg", "chamfer_distance", "chamfer_forward_raw", "emdFunction", "emdModule", "emd_forward_raw",
+    "ChamferDistance", "FilteringChamferDistance", "SegmentingChamferDistance", "EarthMoverDistance",
+    "StatePredictionLoss", "FilterClasses", "ShardedLoss", "shard_bounds",
+]

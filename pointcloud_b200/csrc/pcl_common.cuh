@@ -1,0 +1,61 @@
+// pcl_common.cuh -- shared helpers for libpcl_b200 (sm_100a only).
+#pragma once
+#include <cuda_bf16.h>
+#include <cuda_fp16.h>
+#include <cuda_runtime.h>
+#include <stdint.h>
+#include <stdio.h>
+
+#include "../../include/pcl.h"
+
+#if defined(__CUDA_ARCH__) && (__CUDA_ARCH__ < 1000)
+#error "libpcl_b200 is written for sm_100a (B200) only"
+#endif
+
+namespace pcl {
+
+// thread-local last error text (pcl_last_error)
+void set_error(const char *fmt, ...);
+int cuda_fail(cudaError_t e, const char *what);
+
+#define PCL_CUDA(call)                                        \
+    do {                                                      \
+        cudaError_t _e = (call);                              \
+        if (_e != cudaSuccess) return pcl::cuda_fail(_e, #call); \
+    } while (0)
+
+struct DeviceInfo {
+    int sm_count, cc_major, cc_minor, max_smem_optin;
+};
+int device_info(DeviceInfo *out);  // cached per device
+
+// A strided (B, P, D) point array of fp32 / fp16 / bf16 elements.
+struct Pts {
+    const void *p;
+    int64_t bs, rs;  // element strides
+    int dtype;
+};
+
+template <int DT>
+__device__ __forceinline__ float ld_elem(const void *p, int64_t i) {
+    if constexpr (DT == PCL_F32) return __ldg(reinterpret_cast<const float *>(p) + i);
+    else if constexpr (DT == PCL_F16) return __half2float(__ldg(reinterpret_cast<const __half *>(p) + i));
+    else return __bfloat162float(__ldg(reinterpret_cast<const __nv_bfloat16 *>(p) + i));
+}
+
+// runtime-dtype element load (used in staging loops that are not on the critical path)
+__device__ __forceinline__ float ld_any(const Pts &a, int64_t i) {
+    if (a.dtype == PCL_F32) return ld_elem<PCL_F32>(a.p, i);
+    if (a.dtype == PCL_F16) return ld_elem<PCL_F16>(a.p, i);
+    return ld_elem<PCL_BF16>(a.p, i);
+}
+
+__device__ __forceinline__ float3 ld_xyz(const Pts &a, int64_t b, int64_t row) {
+    const int64_t o = b * a.bs + row * a.rs;
+    return make_float3(ld_any(a, o), ld_any(a, o + 1), ld_any(a, o + 2));
+}
+
+static inline bool dtype_ok(int dt) { return dt == PCL_F32 || dt == PCL_F16 || dt == PCL_BF16; }
+static inline size_t align_up(size_t v, size_t a) { return (v + a - 1) / a * a; }
+
+}  // namespace pcl

@@ -1,0 +1,281 @@
+"""Loss callables -- B200 drop-in for the loss section of pointcloud_vision/utils.py:207-309.
+
+Same class names, constructor arguments, call signature `loss(pred, target) -> 0-d tensor` and the
+optional `.log` attribute protocol (train.py:161 assigns `model.loss_fn.log = model.log`; the loss calls
+`self.log(name, tensor)` with the keys of utils.py:297-298,306-307).
+"""
+from functools import reduce
+
+import torch
+import torch.nn.functional as F
+from torch.autograd import Function
+
+from . import _lib, cfg
+from .chamfer import chamfer_distance
+from .emd_module import emdModule, emd_forward_raw
+
+
+class FilterClasses:
+    """utils.py:110-124: keep the points whose label (column `label_dim`) is in the whitelist."""
+
+    def __init__(self, whitelist, label_dim):
+        self.whitelist = whitelist
+        self.label_dim = label_dim
+
+    def __call__(self, points):
+        label = points[:, self.label_dim].long()  # (N,)
+        mask = reduce(torch.logical_or, [label == v for v in self.whitelist])
+        return points[mask, :]
+
+
+########## Loss Functions ##########
+
+class ChamferDistance:
+    """utils.py:209-211 (all feature channels take part in the distance)."""
+
+    def __call__(self, pred, target):
+        return chamfer_distance(pred, target)[0]
+
+
+class FilteringChamferDistance:
+    """utils.py:213-228: per-cloud class filter of the target, pad + stack, Chamfer with y_lengths.
+
+    With a `FilterClasses` filter the per-cloud Python loop of the reference (utils.py:222-226, one
+    boolean-index + host sync per cloud) is replaced by one batched stable compaction (argsort of the
+    mask) and a single host read of max(num_points); any other callable falls back to the reference's
+    loop."""
+
+    def __init__(self, filter):
+        self.filter = filter
+
+    def _filter_pad(self, target, dtype):
+        f = self.filter
+        if isinstance(f, FilterClasses) and target.dim() == 3:
+            label = target[:, :, f.label_dim].long()                                   # (B, N)
+            mask = reduce(torch.logical_or, [label == v for v in f.whitelist])         # (B, N)
+            num_points = mask.sum(dim=1)                                               # (B,)
+            max_points = int(num_points.max().item()) if mask.shape[0] > 0 else 0
+            order = torch.argsort((~mask).to(torch.uint8), dim=1, stable=True)[:, :max_points]  # kept points first, in order
+            xyz = target[:, :, :3].gather(1, order.unsqueeze(-1).expand(-1, -1, 3)).to(dtype=dtype)
+            keep = torch.arange(max_points, device=target.device)[None, :] < num_points[:, None]
+            xyz = xyz * keep.unsqueeze(-1).to(dtype)                                    # F.pad zeros (utils.py:226)
+            return xyz, num_points
+        filtered = [f(p)[:, :3] for p in target]
+        num_points = [p.shape[0] for p in filtered]
+        max_points = max(num_points)
+        padded = torch.stack([F.pad(p, (0, 0, 0, max_points - p.shape[0])) for p in filtered]).to(dtype=dtype)
+        return padded, torch.tensor(num_points, device=target.device)
+
+    def __call__(self, pred, target):
+        device, dtype = pred.device, torch.float32  # utils.py:218
+        pred = pred.to(dtype=dtype)
+        target, num_points = self._filter_pad(target, dtype)
+        return chamfer_distance(pred, target, y_lengths=num_points.to(device))[0]
+
+
+class SegmentingChamferDistance:
+    """utils.py:230-243: sum over classes of FilteringChamferDistance(pred[class], target)."""
+
+    def __init__(self, class_labels):
+        self.classs_losses = {c: FilteringChamferDistance(FilterClasses([l], label_dim=3)) for c, l in class_labels.items()}
+
+    def __call__(self, pred, target):
+        loss_per_class = torch.stack([loss(pred[c], target) for c, loss in self.classs_losses.items()])
+        return loss_per_class.sum()
+
+
+class _MatchedPointLoss(Function):
+    """point_l = sum(w * sqrt(dist)) / sum(w) with (dist, assignment) from the auction, fused
+    (utils.py:254,292,304 + emd_module.py:63-72).  Returns the two sums so that a batch-sharded caller
+    can all-reduce them before dividing."""
+
+    @staticmethod
+    def forward(ctx, xyz1, xyz2, dist, assignment, matched, class_weights):
+        L = _lib.lib()
+        b, n = dist.shape
+        dev = dist.device
+        c = 0 if class_weights is None else class_weights.numel()
+        with torch.cuda.device(dev):
+            sums = torch.empty(2, device=dev, dtype=torch.float32)
+            wsb = L.pcl_emd_workspace_bytes(b, n)
+            ws = torch.empty(wsb, device=dev, dtype=torch.uint8)
+            rc = L.pcl_emd_weighted_reduce(dist.data_ptr(), _lib.ptr(matched), _lib.ptr(class_weights), b, n, c,
+                                           sums.data_ptr(), ws.data_ptr(), wsb, _lib.stream_ptr())
+            _lib.check(rc, "pcl_emd_weighted_reduce")
+        ctx.save_for_backward(xyz1, xyz2, dist, assignment, matched, class_weights)
+        ctx.in_meta = (xyz1.dtype,)
+        return sums
+
+    @staticmethod
+    def backward(ctx, grad_sums):
+        # Only d/d sums[0] reaches the points (sums[1] depends on labels only).  The kernel computes
+        # grad_xyz1 = g0 * w / (2 sqrt(dist)) * 2 (xyz1 - xyz2[assignment]) with g0 read on the device;
+        # `unit` makes its 1/sums[1] factor a no-op so that the division stays in the autograd graph.
+        xyz1, xyz2, dist, assignment, matched, class_weights = ctx.saved_tensors
+        L = _lib.lib()
+        b, n = dist.shape
+        dev = dist.device
+        c = 0 if class_weights is None else class_weights.numel()
+        g = grad_sums.contiguous().float()
+        with torch.cuda.device(dev):
+            unit = torch.ones(2, device=dev, dtype=torch.float32)
+            grad = torch.empty(b, n, 3, device=dev, dtype=torch.float32)
+            rc = L.pcl_emd_weighted_bwd(*_lib.pts_args(xyz1), *_lib.pts_args(xyz2), b, n, assignment.data_ptr(),
+                                        dist.data_ptr(), _lib.ptr(matched), _lib.ptr(class_weights), c,
+                                        unit.data_ptr(), g.data_ptr(), grad.data_ptr(), _lib.stream_ptr())
+            _lib.check(rc, "pcl_emd_weighted_bwd")
+        if xyz1.shape[2] != 3:
+            full = torch.zeros(xyz1.shape, device=dev, dtype=torch.float32)
+            full[:, :, :3] = grad
+            grad = full
+        return grad.to(ctx.in_meta[0]), None, None, None, None, None
+
+
+def matched_label_hist(target_label, assignment, num_classes):
+    """(hist int64[C], matched int32 (B,N)): labels of the targets each prediction was matched to and
+    their histogram (utils.py:257-258,271-275 -- the bincount of the PERMUTED target labels)."""
+    L = _lib.lib()
+    b, n = assignment.shape
+    dev = assignment.device
+    lab = _lib.as_points(target_label)
+    with torch.cuda.device(dev):
+        hist = torch.empty(num_classes, device=dev, dtype=torch.int64)
+        matched = torch.empty(b, n, device=dev, dtype=torch.int32)
+        rc = L.pcl_emd_match_hist(*_lib.pts_args(lab), assignment.data_ptr(), b, n, num_classes, hist.data_ptr(),
+                                  matched.data_ptr(), _lib.stream_ptr())
+        _lib.check(rc, "pcl_emd_match_hist")
+    return hist, matched
+
+
+class EarthMoverDistance:
+    """utils.py:245-309.  `fused=True` (default) computes the point term with the fused epilogue kernels
+    (matched-label histogram, weighted sqrt-sum, fused backward); `fused=False` follows the reference's
+    torch-op structure line by line on top of emdModule (used by the parity tests -- both must agree).
+
+    `reduce_fn` (optional) is the hook of the batch-sharded wrapper: it is called on the class histogram
+    and on every (numerator, denominator) pair so that they can be all-reduced over the ranks; the default
+    keeps single-GPU semantics."""
+
+    def __init__(self, eps=0.002, its=10000, num_classes=None, feature_weight=0.1, fused=True):
+        self.loss_fn = emdModule()
+        self.eps = eps
+        self.iterations = its
+        self.C = num_classes
+        self.feature_weight = feature_weight  # stored but unused, like the reference (utils.py:251,296)
+        self.fused = fused
+        self.reduce_hist = None   # set by ShardedLoss
+        self.reduce_ratio = None  # set by ShardedLoss
+
+    def log(self, name, value):  # replaced by train.py:161 (`model.loss_fn.log = model.log`)
+        pass
+
+    # -- helpers shared by both paths ---------------------------------------------------------------
+    def _class_weights(self, hist):
+        if self.reduce_hist is not None:
+            hist = self.reduce_hist(hist)
+        distribution = hist / hist.sum()                              # utils.py:274-275
+        class_weights = (1 / (distribution + 1e-4)) ** (1 - 0)        # :285
+        class_weights = class_weights / class_weights.sum()           # :286
+        return distribution, class_weights
+
+    def _ratio(self, num, den):
+        if self.reduce_ratio is not None:
+            return self.reduce_ratio(num, den)
+        return num / den
+
+    def _kl(self, pred, distribution):
+        pred_classes = pred[:, :, 3:].argmax(dim=2)                                  # utils.py:278
+        pred_hist = torch.bincount(pred_classes.view(-1), minlength=self.C)          # :279
+        if self.reduce_hist is not None:
+            pred_hist = self.reduce_hist(pred_hist)
+        pred_distribution = pred_hist / pred_hist.sum()                              # :280
+        return F.kl_div(F.log_softmax(pred_distribution, dim=0), F.softmax(distribution, dim=0), reduction='batchmean')  # :283
+
+    def __call__(self, pred, target):
+        if not self.fused:
+            return self._call_reference_structure(pred, target)
+        if not pred.is_cuda:
+            _lib.require_cuda()
+            pred, target = pred.cuda(), target.cuda()
+        xyz1, xyz2 = _lib.as_points(pred[:, :, :3]), _lib.as_points(target[:, :, :3])
+        dists, assignment, _ = emd_forward_raw(xyz1, xyz2, self.eps, self.iterations)
+
+        if cfg.debug:  # utils.py:261-265
+            num_points = pred.shape[1]
+            num_missing = num_points - assignment.unique().numel()
+            if num_missing / num_points > 0.005:
+                print(f"DEBUG: EMD unassigned = {num_missing} / {num_points} = {num_missing / num_points}")
+
+        if self.C is not None:  # segmentation (utils.py:269-298)
+            hist, matched = matched_label_hist(target[:, :, 3:4], assignment, self.C)
+            distribution, class_weights = self._class_weights(hist)
+            kl_div = self._kl(pred, distribution)
+            class_weights = class_weights.float().contiguous()
+            target_classes = matched.long()
+            # weighted cross entropy == sum_i w_i * nll_i / sum_i w_i  (F.cross_entropy with weight=, utils.py:295)
+            logp = F.log_softmax(pred[:, :, 3:].float(), dim=2)
+            nll = -logp.gather(2, target_classes.unsqueeze(-1)).squeeze(-1)
+            w = class_weights[target_classes]
+            ce_l = self._ratio((nll * w).sum(), w.sum())
+            feature_l = 0.1 * ce_l
+            self.log('train_loss/cross_entropy', ce_l)
+            self.log('train_loss/kl_divergence', kl_div)
+            sums = _MatchedPointLoss.apply(xyz1, xyz2, dists, assignment, matched, class_weights)
+        else:  # general feature loss (utils.py:300-301)
+            idx = assignment.long().unsqueeze(-1)
+            matched_feat = target[:, :, 3:].take_along_dim(idx, 1)
+            diff = pred[:, :, 3:] - matched_feat
+            numel = diff.numel()
+            if numel == 0:
+                feature_l = F.mse_loss(pred[:, :, 3:], matched_feat)  # nan, exactly like the reference on empty features
+            else:
+                feature_l = self._ratio((diff * diff).sum(), torch.tensor(float(numel), device=pred.device))
+            sums = _MatchedPointLoss.apply(xyz1, xyz2, dists, assignment, None, None)
+
+        point_l = self._ratio(sums[0], sums[1])  # utils.py:304
+        self.log('train_loss/EMD', point_l)
+        self.log('train_loss/feature', feature_l)
+        return point_l + feature_l
+
+    # -- the reference's own structure, op by op (utils.py:253-309) ----------------------------------
+    def _call_reference_structure(self, pred, target):
+        dists, assignment = self.loss_fn(pred[:, :, :3], target[:, :, :3], self.eps, self.iterations)
+        assignment = assignment.long().unsqueeze(-1)
+        target = target.to(dists.device).take_along_dim(assignment, 1)
+        pred = pred.to(dists.device)
+        weights = torch.ones_like(dists)  # (B, N)
+        if self.C is not None:
+            target_classes = target[:, :, 3].long()
+            distribution = torch.bincount(target_classes.view(-1), minlength=self.C)
+            distribution = distribution / distribution.sum()
+            pred_classes = pred[:, :, 3:].argmax(dim=2)
+            pred_distribution = torch.bincount(pred_classes.view(-1), minlength=self.C)
+            pred_distribution = pred_distribution / pred_distribution.sum()
+            kl_div = F.kl_div(F.log_softmax(pred_distribution, dim=0), F.softmax(distribution, dim=0), reduction='batchmean')
+            class_weights = (1 / (distribution + 1e-4)) ** (1 - 0)
+            class_weights = class_weights / class_weights.sum()
+            weights = class_weights[target_classes]
+            ce_l = F.cross_entropy(pred.permute(0, 2, 1)[:, 3:, :].float(), target_classes, weight=class_weights)
+            feature_l = 0.1 * ce_l
+            self.log('train_loss/cross_entropy', ce_l)
+            self.log('train_loss/kl_divergence', kl_div)
+        else:
+            feature_l = F.mse_loss(pred[:, :, 3:], target[:, :, 3:])
+        point_l = (dists.sqrt() * weights).sum() / weights.sum()
+        self.log('train_loss/EMD', point_l)
+        self.log('train_loss/feature', feature_l)
+        return point_l + feature_l
+
+
+class StatePredictionLoss:
+    """utils.py:311-321 (not on the hot path; kept so that `create_model` finds every loss in one module)."""
+
+    def __init__(self, states, transforms):
+        self.state_losses = {s: F.mse_loss for s in states}
+        self.t = transforms
+        for s in states:
+            if s not in self.t:
+                self.t[s] = lambda x: x
+
+    def __call__(self, pred, target):
+        return torch.stack([loss(pred[s], self.t[s](target[s])) for s, loss in self.state_losses.items()]).mean()
