@@ -93,8 +93,6 @@ def as_points(t: torch.Tensor) -> torch.Tensor:
         raise ValueError(f"expected a (B, P, D) tensor, got shape {tuple(t.shape)}")
     if t.shape[2] > 1 and t.stride(2) != 1:
         t = t.contiguous()
-    elif t.shape[2] == 1 and t.stride(2) != 1:
-        t = t.contiguous()
     return t
 
 

@@ -191,14 +191,25 @@ class EarthMoverDistance:
         pred_distribution = pred_hist / pred_hist.sum()                              # :280
         return F.kl_div(F.log_softmax(pred_distribution, dim=0), F.softmax(distribution, dim=0), reduction='batchmean')  # :283
 
+    # -- the three places where the fused path enters the CUDA library (overridden only by CPU host-logic tests)
+    def _auction(self, pred, target):
+        xyz1, xyz2 = _lib.as_points(pred[:, :, :3]), _lib.as_points(target[:, :, :3])
+        dists, assignment, _ = emd_forward_raw(xyz1, xyz2, self.eps, self.iterations)
+        return xyz1, xyz2, dists, assignment
+
+    def _matched_hist(self, target, assignment):
+        return matched_label_hist(target[:, :, 3:4], assignment, self.C)
+
+    def _point_sums(self, xyz1, xyz2, dists, assignment, matched, class_weights):
+        return _MatchedPointLoss.apply(xyz1, xyz2, dists, assignment, matched, class_weights)
+
     def __call__(self, pred, target):
         if not self.fused:
             return self._call_reference_structure(pred, target)
-        if not pred.is_cuda:
+        if not pred.is_cuda and type(self)._auction is EarthMoverDistance._auction:
             _lib.require_cuda()
             pred, target = pred.cuda(), target.cuda()
-        xyz1, xyz2 = _lib.as_points(pred[:, :, :3]), _lib.as_points(target[:, :, :3])
-        dists, assignment, _ = emd_forward_raw(xyz1, xyz2, self.eps, self.iterations)
+        xyz1, xyz2, dists, assignment = self._auction(pred, target)
 
         if cfg.debug:  # utils.py:261-265
             num_points = pred.shape[1]
@@ -207,7 +218,7 @@ class EarthMoverDistance:
                 print(f"DEBUG: EMD unassigned = {num_missing} / {num_points} = {num_missing / num_points}")
 
         if self.C is not None:  # segmentation (utils.py:269-298)
-            hist, matched = matched_label_hist(target[:, :, 3:4], assignment, self.C)
+            hist, matched = self._matched_hist(target, assignment)
             distribution, class_weights = self._class_weights(hist)
             kl_div = self._kl(pred, distribution)
             class_weights = class_weights.float().contiguous()
@@ -220,7 +231,7 @@ class EarthMoverDistance:
             feature_l = 0.1 * ce_l
             self.log('train_loss/cross_entropy', ce_l)
             self.log('train_loss/kl_divergence', kl_div)
-            sums = _MatchedPointLoss.apply(xyz1, xyz2, dists, assignment, matched, class_weights)
+            sums = self._point_sums(xyz1, xyz2, dists, assignment, matched, class_weights)
         else:  # general feature loss (utils.py:300-301)
             idx = assignment.long().unsqueeze(-1)
             matched_feat = target[:, :, 3:].take_along_dim(idx, 1)
@@ -230,7 +241,7 @@ class EarthMoverDistance:
                 feature_l = F.mse_loss(pred[:, :, 3:], matched_feat)  # nan, exactly like the reference on empty features
             else:
                 feature_l = self._ratio((diff * diff).sum(), torch.tensor(float(numel), device=pred.device))
-            sums = _MatchedPointLoss.apply(xyz1, xyz2, dists, assignment, None, None)
+            sums = self._point_sums(xyz1, xyz2, dists, assignment, None, None)
 
         point_l = self._ratio(sums[0], sums[1])  # utils.py:304
         self.log('train_loss/EMD', point_l)

@@ -1,0 +1,40 @@
+"""Shared helpers for the GPU parity tests."""
+import numpy as np
+import torch
+
+
+def ref_emd_forward(ref, xyz1, xyz2, eps, iters):
+    """Call the UNMODIFIED reference extension exactly like emdFunction.forward does (emd_module.py:43-58)."""
+    b, n, _ = xyz1.shape
+    dev = 'cuda'
+    xyz1, xyz2 = xyz1.contiguous().float().cuda(), xyz2.contiguous().float().cuda()
+    dist = torch.zeros(b, n, device=dev)
+    assignment = torch.zeros(b, n, device=dev, dtype=torch.int32) - 1
+    assignment_inv = torch.zeros(b, n, device=dev, dtype=torch.int32) - 1
+    price = torch.zeros(b, n, device=dev)
+    bid = torch.zeros(b, n, device=dev, dtype=torch.int32)
+    bid_increments = torch.zeros(b, n, device=dev)
+    max_increments = torch.zeros(b, n, device=dev)
+    unass_idx = torch.zeros(b * n, device=dev, dtype=torch.int32)
+    max_idx = torch.zeros(b * n, device=dev, dtype=torch.int32)
+    unass_cnt = torch.zeros(512, dtype=torch.int32, device=dev)
+    unass_cnt_sum = torch.zeros(512, dtype=torch.int32, device=dev)
+    cnt_tmp = torch.zeros(512, dtype=torch.int32, device=dev)
+    ref.forward(xyz1, xyz2, dist, assignment, price, assignment_inv, bid, bid_increments, max_increments,
+                unass_idx, unass_cnt, unass_cnt_sum, cnt_tmp, max_idx, eps, iters)
+    return dist, assignment
+
+
+def ref_emd_backward(ref, xyz1, xyz2, graddist, assignment):
+    gradxyz1 = torch.zeros(xyz1.size(), device='cuda')
+    ref.backward(xyz1.contiguous().float().cuda(), xyz2.contiguous().float().cuda(), gradxyz1, graddist.contiguous(), assignment)
+    return gradxyz1
+
+
+def npy(t):
+    return t.detach().cpu().numpy()
+
+
+def sqdist_to_match(x1, x2, asg):
+    m = np.take_along_axis(np.asarray(x2), np.asarray(asg).astype(np.int64)[..., None], 1)
+    return ((np.asarray(x1, dtype=np.float64) - m) ** 2).sum(-1)

@@ -1,0 +1,160 @@
+"""GPU tests of the loss callables (the drop-in surface of pointcloud_vision/utils.py:207-309): fused path
+vs the reference-structure path vs the golden vectors of the real reference Python, the `.log` protocol,
+mixed precision, SegmentingChamferDistance, the host-buffer C entry point and the sharded wrapper on one rank."""
+import ctypes
+
+import numpy as np
+import pytest
+import torch
+
+import pointcloud_b200 as pcl
+from oracle import loss_oracle
+from pointcloud_b200 import synth
+from helpers import npy
+
+pytestmark = pytest.mark.gpu
+REL = 1e-5
+
+
+def _t(a):
+    return torch.from_numpy(np.asarray(a))
+
+
+@pytest.mark.parametrize("fused", [True, False])
+@pytest.mark.parametrize("tag,C", [("ae", None), ("seg", 5)])
+def test_earth_mover_distance_matches_reference_python_golden(golden, tag, C, fused):
+    pred = _t(golden[f"{tag}_pred"]).cuda().requires_grad_()
+    fn = pcl.EarthMoverDistance(eps=0.005, its=50, num_classes=C, fused=fused)
+    logged = {}
+    fn.log = lambda k, v: logged.__setitem__(k, float(v.detach()))     # train.py:161
+    loss = fn(pred, _t(golden[f"{tag}_target"]).cuda())
+    assert loss.dim() == 0 and loss.device.type == "cuda"
+    loss.backward()
+    assert float(loss) == pytest.approx(float(golden[f"{tag}_loss"]), rel=REL)
+    keys = ["EMD", "feature"] + (["cross_entropy", "kl_divergence"] if C else [])
+    assert set(logged) == {f"train_loss/{k}" for k in keys}
+    for k in keys:
+        assert logged[f"train_loss/{k}"] == pytest.approx(float(golden[f"{tag}_log_{k}"]), rel=REL)
+    np.testing.assert_allclose(npy(pred.grad), golden[f"{tag}_grad"], rtol=REL, atol=1e-10)
+
+
+@pytest.mark.parametrize("C", [None, 5])
+def test_fused_and_reference_structure_agree_at_full_size(C):
+    """BASELINE configs 2/3: B=32, N=2048, train settings."""
+    pred, target = (synth.segmenter_batch if C else synth.autoencoder_batch)(32, 2048, seed=4, regime="noisy")
+    out = []
+    for fused in (True, False):
+        p = pred.cuda().requires_grad_()
+        loss = pcl.EarthMoverDistance(0.005, 50, num_classes=C, fused=fused)(p, target.cuda())
+        loss.backward()
+        out.append((float(loss), npy(p.grad)))
+    assert out[0][0] == pytest.approx(out[1][0], rel=REL)
+    np.testing.assert_allclose(out[0][1], out[1][1], rtol=REL, atol=1e-10)
+    assert np.isfinite(out[0][1]).all()
+
+
+def test_earth_mover_distance_vs_loss_oracle_small_segmenter():
+    pred, target = synth.segmenter_batch(3, 1024, seed=8)
+    po = pred.clone().requires_grad_()
+    lo = loss_oracle.EarthMoverDistance(0.005, 50, num_classes=5)(po, target)
+    lo.backward()
+    pg = pred.cuda().requires_grad_()
+    lg = pcl.EarthMoverDistance(0.005, 50, num_classes=5)(pg, target.cuda())
+    lg.backward()
+    assert float(lg) == pytest.approx(float(lo), rel=REL)
+    np.testing.assert_allclose(npy(pg.grad), po.grad.numpy(), rtol=REL, atol=1e-10)
+
+
+def test_mixed_precision_prediction():
+    """cfg.precision = '16-mixed': the model output may arrive as fp16/bf16; the kernels up-cast like .float()."""
+    pred, target = synth.autoencoder_batch(2, 1024, seed=9)
+    for dt in (torch.float16, torch.bfloat16):
+        ph = pred.cuda().to(dt).requires_grad_()
+        loss = pcl.EarthMoverDistance(0.005, 50)(ph, target.cuda())
+        loss.backward()
+        pf = ph.detach().float().requires_grad_()
+        lf = pcl.EarthMoverDistance(0.005, 50)(pf, target.cuda())
+        lf.backward()
+        assert ph.grad.dtype == dt
+        assert float(loss) == pytest.approx(float(lf), rel=2e-3)
+        np.testing.assert_allclose(npy(ph.grad.float()[:, :, :3]), npy(pf.grad[:, :, :3]), rtol=2e-2, atol=1e-6)
+
+
+def test_segmenting_chamfer_distance_golden_and_oracle(golden):
+    labels = {nm: i for i, nm in enumerate(["env", "cube", "arm", "base", "gripper"])}
+    pred = {k: _t(golden[f"mseg_pred_{k}"]).cuda().requires_grad_() for k in labels}
+    loss = pcl.SegmentingChamferDistance(labels)(pred, _t(golden["mseg_target"]).cuda())
+    loss.backward()
+    assert float(loss) == pytest.approx(float(golden["mseg_loss"]), rel=REL)
+    for k in labels:
+        np.testing.assert_allclose(npy(pred[k].grad), golden[f"mseg_grad_{k}"], rtol=REL, atol=1e-9)
+    # full-size MultiSegmenter batch (P_c = 21/820/103... of 2048, variable-length targets) vs the oracle
+    pd, target, labels = synth.multisegmenter_batch(8, 2048, seed=6)
+    po = {k: v.clone().requires_grad_() for k, v in pd.items()}
+    lo = loss_oracle.SegmentingChamferDistance(labels)(po, target)
+    lo.backward()
+    pg = {k: v.cuda().requires_grad_() for k, v in pd.items()}
+    lg = pcl.SegmentingChamferDistance(labels)(pg, target.cuda())
+    lg.backward()
+    assert float(lg) == pytest.approx(float(lo), rel=REL)
+    for k in labels:
+        np.testing.assert_allclose(npy(pg[k].grad), po[k].grad.numpy(), rtol=REL, atol=1e-9)
+    # a custom (non-FilterClasses) filter takes the reference's per-cloud loop and must agree with the batched one
+    f = pcl.FilterClasses([2], label_dim=3)
+    a = pcl.FilteringChamferDistance(f)(pg["arm"].detach(), target.cuda())
+    b = pcl.FilteringChamferDistance(lambda p: f(p))(pg["arm"].detach(), target.cuda())
+    assert float(a) == pytest.approx(float(b), rel=1e-6)
+
+
+def test_sqrt_at_zero_distance_behaves_like_the_reference():
+    """utils.py:304: dists.sqrt() has an infinite derivative at 0 -- the reference yields non-finite grads when a
+    prediction coincides with its match; the fused path must not silently hide that."""
+    _, target = synth.autoencoder_batch(1, 1024, seed=3)
+    for fused in (True, False):
+        p = target.clone().cuda().requires_grad_()
+        loss = pcl.EarthMoverDistance(0.005, 50, fused=fused)(p, target.cuda())
+        loss.backward()
+        assert float(loss) == pytest.approx(0.0, abs=1e-6)
+        assert not torch.isfinite(p.grad[:, :, :3]).all()
+
+
+def test_host_buffer_step_entry_point_matches_device_path():
+    """pcl_chamfer_emd_step_host: pinned host buffers in, losses + gradients out (what a non-torch caller binds)."""
+    from pointcloud_b200 import _lib
+    L = _lib.lib()
+    b, n = 4, 1024
+    x1, x2 = synth.uniform_clouds(b, n, seed=12)
+    ph, th = x1.pin_memory(), x2.pin_memory()
+    loss_h = torch.zeros(3).pin_memory()
+    gch, geh = torch.zeros(b, n, 3).pin_memory(), torch.zeros(b, n, 3).pin_memory()
+    nbytes = L.pcl_loss_host_scratch_bytes(b, n)
+    scratch = torch.empty(nbytes, dtype=torch.uint8, device="cuda")
+    st = torch.cuda.current_stream().cuda_stream
+    rc = L.pcl_chamfer_emd_step_host(ph.data_ptr(), th.data_ptr(), b, n, 0.005, 50, 0, loss_h.data_ptr(), gch.data_ptr(),
+                                     geh.data_ptr(), scratch.data_ptr(), nbytes, st)
+    assert rc == 0, L.pcl_last_error()
+    torch.cuda.synchronize()
+    xg = x1.cuda().requires_grad_()
+    cl, _ = pcl.chamfer_distance(xg, x2.cuda())
+    cl.backward()
+    assert float(loss_h[0] + loss_h[1]) == pytest.approx(float(cl), rel=1e-6)
+    np.testing.assert_allclose(gch.numpy(), npy(xg.grad), rtol=REL, atol=1e-9)
+    xe = x1.cuda().requires_grad_()
+    dist, _ = pcl.emdModule()(xe, x2.cuda(), 0.005, 50)
+    el = dist.sqrt().mean()
+    el.backward()
+    assert float(loss_h[2]) == pytest.approx(float(el), rel=1e-6)
+    np.testing.assert_allclose(geh.numpy(), npy(xe.grad), rtol=REL, atol=1e-10)
+    rc = L.pcl_chamfer_emd_step_host(ph.data_ptr(), th.data_ptr(), b, n, 0.005, 50, 0, loss_h.data_ptr(), None, None,
+                                     scratch.data_ptr(), 16, st)
+    assert rc == -4 and b"scratch" in L.pcl_last_error()
+
+
+def test_sharded_wrapper_single_rank_is_identity():
+    pred, target = synth.segmenter_batch(4, 1024, seed=2)
+    p1, p2 = pred.cuda().requires_grad_(), pred.cuda().requires_grad_()
+    a = pcl.EarthMoverDistance(0.005, 50, num_classes=5)(p1, target.cuda())
+    b = pcl.ShardedLoss(pcl.EarthMoverDistance(0.005, 50, num_classes=5))(p2, target.cuda())
+    a.backward(); b.backward()
+    assert float(a) == pytest.approx(float(b), rel=1e-6)
+    np.testing.assert_allclose(npy(p1.grad), npy(p2.grad), rtol=1e-6, atol=1e-12)
