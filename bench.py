@@ -220,6 +220,7 @@ def main():
     ap.add_argument("--warmup", type=int, default=5)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--profile", action="store_true", help="value leg + breakdown only (short command for ncu)")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3)
     if args.impl == "reference":
@@ -313,6 +314,13 @@ def main():
     breakdown["chamfer_directed_pair_evals_per_s"] = ch_evals / (breakdown["chamfer_fwd_bwd"] * 1e-3)
 
     # ---- e2e: public Python API, pinned host inputs -> device, loss scalars -> host, every step -----------
+    if args.profile:
+        if rank == 0:
+            print(json.dumps({"metric": METRIC, "value": value, "unit": UNIT, "ms_per_step": ms_per_step, "profile_run": True,
+                              "breakdown_ms": breakdown, "roofline": roofline}))
+        if world > 1:
+            dist.destroy_process_group()
+        return
     host = [(p.cpu().pin_memory(), t.cpu().pin_memory()) for p, t, _ in pool[:16]]
     emd_mod = pcl.emdModule()
 

@@ -46,7 +46,7 @@ chamfer_nn3_kernel(Pts x, const int64_t *__restrict__ x_len, Pts y, const int64_
     __shared__ float red[4];
     const int dir = blockIdx.z, n = blockIdx.y;
     const Pts q = dir ? y : x, t = dir ? x : y;
-    const int PQ = dir ? P2 : P1, PT = dir ? P1 : P2;
+    const int PQ = dir ? P2 : P1;
     const int q0 = blockIdx.x * (CH_THREADS * QPT);
     if (q0 >= PQ) return;  // block-uniform
     const int lq = dir ? (y_len ? (int)y_len[n] : P2) : (x_len ? (int)x_len[n] : P1);

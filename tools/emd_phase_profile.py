@@ -1,0 +1,40 @@
+"""Development aid: per-phase clock totals of the auction kernel (PCL_EMD_PROFILE=1)."""
+import os, sys
+os.environ["PCL_EMD_PROFILE"] = "1"
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+import torch
+import pointcloud_b200 as pcl
+from pointcloud_b200 import _lib, synth
+
+L = _lib.lib()
+names = ["init", "compact", "bid", "cluster_wait", "resolve", "epilogue"]
+for kind in ("uniform", "table", "noisy"):
+    b, n = 32, 2048
+    if kind == "uniform":
+        x1, x2 = synth.uniform_clouds(b, n, seed=0)
+    else:
+        x1, t = synth.table_clouds(b, n, seed=0, regime="independent" if kind == "table" else "noisy")
+        x2 = t[:, :, :3].contiguous()
+    x1, x2 = x1.cuda(), x2.cuda()
+    dist = torch.empty(b, n, device="cuda"); asg = torch.empty(b, n, device="cuda", dtype=torch.int32)
+    stats = torch.empty(b, 4, device="cuda", dtype=torch.int32)
+    wsb = L.pcl_emd_workspace_bytes(b, n); ws = torch.zeros(wsb, device="cuda", dtype=torch.uint8)
+    for _ in range(3):
+        ws.zero_()
+        rc = L.pcl_emd_fwd(*_lib.pts_args(x1), *_lib.pts_args(x2), b, n, 0.005, 50, dist.data_ptr(), asg.data_ptr(), stats.data_ptr(), ws.data_ptr(), wsb, None)
+        assert rc == 0
+    torch.cuda.synchronize()
+    cs = int(stats[0, 3])
+    prof = ws.view(torch.int64)[: b * cs * 8].view(b, cs, 8).double().cpu()
+    tot = prof.sum(-1)
+    print(f"{kind}: cs={cs} iters_run={stats[:,1].tolist()[:6]}.. per-CTA total cycles mean={tot.mean():.0f} max={tot.max():.0f}")
+    for i, nm in enumerate(names):
+        print(f"   {nm:13s} mean {prof[:,:,i].mean():10.0f} cyc ({100*prof[:,:,i].mean()/tot.mean():5.1f}%)  max {prof[:,:,i].max():10.0f}")
+    it = ws.view(torch.int64)[b * cs * 8: b * cs * 8 + 100].view(50, 2).cpu()
+    print("   per-iteration (U, bid cycles of CTA0):", [(int(u), int(c)) for u, c in it.tolist()][:50])
+    sub = ws.view(torch.int64)[b * cs * 8 + 128: b * cs * 8 + 128 + 200].view(50, 4).cpu()
+    print("   sub-phase ticks (after load, init, scan, sync) per iteration:", sub.tolist()[:50:3])
+    cnt = ws.view(torch.int64)[b * cs * 8 + 400: b * cs * 8 + 408].cpu().tolist()
+    for nm, c in (("iteration 0", cnt[:3]), ("iterations >= 1", cnt[4:7])):
+        ev, sg, ex = c
+        print(f"   {nm}: evals={ev} slow groups={sg} ({100*sg/max(ev/4,1):.1f}% of groups) exact evals={ex} ({100*ex/max(ev,1):.2f}% of evals)")
