@@ -128,7 +128,7 @@ class DeviceStep:
         self.dist_x, self.dist_y, self.idx_x, self.idx_y = e(b, n), e(b, n), e(b, n, dt=i32), e(b, n, dt=i32)
         self.loss_xy, self.ones = e(2), torch.ones(2, device=device)
         self.gx, self.gy = e(b, n, 3), e(b, n, 3)
-        self.dist, self.asg, self.stats = e(b, n), e(b, n, dt=i32), e(b, 4, dt=i32)
+        self.dist, self.asg, self.stats = e(b, n), e(b, n, dt=i32), e(b, 8, dt=i32)
         self.sums, self.gemd = e(2), e(b, n, 3)
         self.cws = self.L.pcl_chamfer_workspace_bytes(b, n, n); self.cw = torch.empty(self.cws, device=device, dtype=torch.uint8)
         self.ews = self.L.pcl_emd_workspace_bytes(b, n); self.ew = torch.empty(self.ews, device=device, dtype=torch.uint8)

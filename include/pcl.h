@@ -95,7 +95,9 @@ PCL_API int pcl_chamfer_bwd(const void *x, int x_dtype, int64_t x_bs, int64_t x_
  * {list unassigned, Bid, GetMax, Assign} then CalcDist, all inside ONE persistent kernel.
  *   xyz1 = prediction (B,N,3) (receives the gradient), xyz2 = target (B,N,3), both in [0,1]^3.
  *   dist (B,N) fp32 = squared distance to the matched target, assignment (B,N) int32.
- *   stats: nullable int32[B*4] = { sum_t U_t, iterations run, GetMax multi-bidder events, cluster size }.
+ *   stats: nullable int32[B*8] = { sum_t U_t, iterations run, GetMax multi-bidder events, cluster size,
+ *          executed pair evaluations (lo, hi 32 bits; tiles skipped by the spatial pruning are not counted),
+ *          launch flags, tiles per cloud }.
  * Constraints: 1 <= N <= pcl_emd_max_points(), B >= 0 (the reference needs N%1024==0 and B<=512,
  * emd_cuda.cu:241-249; both are accepted here, neither is required).
  * The GetMax race of the reference (emd_cuda.cu:188-191) is resolved deterministically: the

@@ -37,51 +37,67 @@ namespace pcl {
 namespace {
 
 constexpr int EMD_THREADS = 512;
+constexpr int EMD_WARPS = EMD_THREADS / 32;
 constexpr int EMD_MAX_N = 4096;
+constexpr int TILE = 32;  // targets per spatial tile (one bounding box per tile)
+constexpr int EMD_WPB_MAX = 4 * EMD_WARPS;  // at most this many bidders per CTA: warp-per-bidder scan
 constexpr unsigned short NONE16 = 0xffffu;
 constexpr unsigned NOLAST = 0xffffffffu;
 constexpr float FILTER_MARGIN = 2e-6f;  // > 4.2e-7 worst-case rounding slack of the filter
 
+// flags of the launch (what fits into shared memory for this N)
+constexpr int EMD_F_SORT = 1;  // clouds are re-ordered along a Morton curve inside the kernel
+constexpr int EMD_F_X1 = 2;    // predictions are cached in shared memory
+
 struct EmdSmem {
-    float4 *tgt;            // N   {x, y, z, c = RU(3 - price)}
+    float4 *tgt;            // n32 {x, y, z, c = RU(3 - price)}, internal (sorted) target order, padded with far sentinels
+    uint2 *pub;             // 2N  published bids {object | second<<16, increment bits}, double-buffered (sort scratch at init)
     float *pf;              // N   price (fp32, as in the reference)
-    uint2 *pub;             // 2N  published bids {object | second<<16, increment bits}, double-buffered
     float *maxinc;          // N   per-object running max increment (reference: max_increments)
-    int *maxidx;            // N   per-object winning bidder (reference: max_idx), -1 = none
+    int *maxidx;            // N   per-object winning bidder, ORIGINAL index (reference: max_idx), -1 = none
     unsigned *last;         // N   previous bid of every bidder (object | second<<16), NOLAST = never bid
-    unsigned short *asg;    // N8  assignment (pred j -> target), NONE16 = unassigned; padded with 0
+    unsigned short *asg;    // N8  assignment (pred -> target, internal indices), NONE16 = unassigned; padded with 0
     unsigned short *inv;    // N   assignment_inv (target -> pred), NONE16 = free
-    unsigned short *unass;  // N   compacted list of unassigned bidders
-    float *pbest, *pbetter; // T   chunk partials
-    unsigned *pbi;          // T
+    unsigned short *unass;  // N   compacted list of unassigned bidders (internal pred indices, ascending)
+    float *pbest, *pbetter; // pcap slice partials (pcap = 32 * max work items with a partial)
+    unsigned *pbi;          // pcap
     int *wsum;              // 32
-    float4 *x1;             // N   predictions {x,y,z,0} when they fit (else nullptr: read from global/L2)
+    unsigned long long *evals;  // 1   executed evaluations of the whole cluster (accumulated in rank 0's copy)
+    float4 *tlo, *thi;      // NT  tile boxes: lo = {min xyz, max c of the tile}, hi = {max xyz, -}
+    unsigned short *tperm;  // N   internal target index -> original index (nullptr: identity)
+    unsigned short *pperm;  // N   internal pred index -> original index (nullptr: identity)
+    float4 *x1;             // N   predictions {x,y,z,0} in internal order (nullptr: read from global/L2)
 };
 
-__host__ __device__ inline size_t emd_smem_bytes(int N, bool with_x1) {
-    const size_t n8 = (size_t)(N + 7) / 8 * 8;
-    return n8 * (16 + 4 + 16 + 4 + 4 + 4) + n8 * 2 * 3 + (size_t)EMD_THREADS * 12 + 32 * 4 + 64 + (with_x1 ? n8 * 16 : 0);
+__host__ __device__ inline size_t emd_smem_bytes(int N, int flags, int pcap = EMD_THREADS) {
+    const size_t n8 = (size_t)(N + 7) / 8 * 8, n32 = (size_t)(N + 31) / 32 * 32, nt = n32 / 32;
+    return n32 * 16 + n8 * (16 + 4 + 4 + 4 + 4) + n8 * 2 * 3 + (size_t)pcap * 12 + 32 * 4 + 16 + nt * 32 +
+           ((flags & EMD_F_SORT) ? n8 * 4 : 0) + ((flags & EMD_F_X1) ? n8 * 16 : 0) + 64;
 }
 
-__device__ inline EmdSmem carve(unsigned char *base, int N, bool with_x1) {
-    const size_t n8 = (size_t)(N + 7) / 8 * 8;
+__device__ inline EmdSmem carve(unsigned char *base, int N, int flags, int pcap) {
+    const size_t n8 = (size_t)(N + 7) / 8 * 8, n32 = (size_t)(N + 31) / 32 * 32, nt = n32 / 32;
     EmdSmem s;
     unsigned char *p = base;
-    s.tgt = (float4 *)p; p += n8 * 16;
+    s.tgt = (float4 *)p; p += n32 * 16;
     s.pub = (uint2 *)p; p += n8 * 16;
+    s.tlo = (float4 *)p; p += nt * 16;
+    s.thi = (float4 *)p; p += nt * 16;
+    s.x1 = (flags & EMD_F_X1) ? (float4 *)p : nullptr; p += (flags & EMD_F_X1) ? n8 * 16 : 0;
     s.asg = (unsigned short *)p; p += n8 * 2;   // 16-byte aligned for the uint4 reads of the compaction
     s.inv = (unsigned short *)p; p += n8 * 2;
     s.unass = (unsigned short *)p; p += n8 * 2;
+    s.tperm = (flags & EMD_F_SORT) ? (unsigned short *)p : nullptr; p += (flags & EMD_F_SORT) ? n8 * 2 : 0;
+    s.pperm = (flags & EMD_F_SORT) ? (unsigned short *)p : nullptr; p += (flags & EMD_F_SORT) ? n8 * 2 : 0;
     s.pf = (float *)p; p += n8 * 4;
     s.maxinc = (float *)p; p += n8 * 4;
     s.maxidx = (int *)p; p += n8 * 4;
     s.last = (unsigned *)p; p += n8 * 4;
-    s.pbest = (float *)p; p += EMD_THREADS * 4;
-    s.pbetter = (float *)p; p += EMD_THREADS * 4;
-    s.pbi = (unsigned *)p; p += EMD_THREADS * 4;
+    s.pbest = (float *)p; p += (size_t)pcap * 4;
+    s.pbetter = (float *)p; p += (size_t)pcap * 4;
+    s.pbi = (unsigned *)p; p += (size_t)pcap * 4;
     s.wsum = (int *)p; p += 32 * 4;
-    p = (unsigned char *)(((uintptr_t)p + 15) & ~(uintptr_t)15);
-    s.x1 = with_x1 ? (float4 *)p : nullptr;
+    s.evals = (unsigned long long *)p; p += 16;
     return s;
 }
 
@@ -100,57 +116,93 @@ __device__ __forceinline__ float bid_value_exact(float s, float price) {
     return __double2float_rn(__dsub_rn(__dsub_rn(3.0, (double)__fsqrt_rn(s)), (double)price));
 }
 
+// 18-bit Morton code of a point (6 bits per axis over [0,1]); only the spatial coherence of the internal
+// order depends on it, never a result.
+__device__ __forceinline__ unsigned spread6(unsigned v) {
+    v = (v | (v << 8)) & 0x0000300Fu;
+    v = (v | (v << 4)) & 0x000030C3u;
+    v = (v | (v << 2)) & 0x00009249u;
+    return v;
+}
+__device__ __forceinline__ unsigned morton18(float3 p) {
+    const unsigned qx = (unsigned)min(max((int)(p.x * 64.f), 0), 63), qy = (unsigned)min(max((int)(p.y * 64.f), 0), 63),
+                   qz = (unsigned)min(max((int)(p.z * 64.f), 0), 63);
+    return spread6(qx) | (spread6(qy) << 1) | (spread6(qz) << 2);
+}
+
+// in-place ascending bitonic sort of np (power of two) unique 32-bit keys in shared memory, whole CTA
+__device__ inline void bitonic_sort(unsigned *keys, int np) {
+    for (int k = 2; k <= np; k <<= 1) {
+        for (int j = k >> 1; j > 0; j >>= 1) {
+            for (int i = threadIdx.x; i < (np >> 1); i += EMD_THREADS) {
+                const int lo = ((i & ~(j - 1)) << 1) | (i & (j - 1)), hi = lo | j;
+                const unsigned a = keys[lo], b = keys[hi];
+                const bool up = ((lo & k) == 0);
+                if ((a > b) == up) { keys[lo] = b; keys[hi] = a; }
+            }
+            __syncthreads();
+        }
+    }
+}
+
 struct Top2 {
     float best, better;  // emd_cuda.cu:112
-    int bi, bi2;         // first argmax (the bid) and the index of the runner-up (seed for the next bid)
+    int bi, bi2;         // internal index of the bid (first argmax in ORIGINAL index order) and of the runner-up
+    int bio;             // original index of bi (tie rule: lowest original index among equal maxima)
     float tm;            // filter threshold: (lower bound of the final second best) - margin
-    int n_exact, n_slowgrp;  // statistics (profiling build only; dead code otherwise)
 };
 
-__device__ __forceinline__ void top2_exact(Top2 &r, float s, float price, int k) {
-    r.n_exact++;
-    const float v = bid_value_exact(s, price);
-    if (v > r.best) { r.better = r.best; r.bi2 = r.bi; r.best = v; r.bi = k; }  // emd_cuda.cu:147-151
-    else if (v > r.better) { r.better = v; r.bi2 = k; }                           // :152-154
+// Exact update.  Order-independent restatement of emd_cuda.cu:147-154 scanned in ascending original index:
+// best = max value, its index = lowest original index attaining it, better = second largest counting duplicates.
+__device__ __forceinline__ void top2_exact(const EmdSmem &S, Top2 &r, float s, int k) {
+    const float v = bid_value_exact(s, S.pf[k]);
+    const int ko = S.tperm ? (int)S.tperm[k] : k;
+    if (v > r.best || (v == r.best && ko < r.bio)) { r.better = r.best; r.bi2 = r.bi; r.best = v; r.bi = k; r.bio = ko; }
+    else if (v > r.better) { r.better = v; r.bi2 = k; }
     r.tm = fmaxf(r.tm, __fsub_rn(r.better, FILTER_MARGIN));
 }
 
-// Scan targets [k0,k1) for the bidder at (ax,ay,az).  e = u*u - s with u = c_k - tm: e < 0 proves
-// value_k < (final second best), so the candidate cannot change best / second best / first argmax.
-__device__ __forceinline__ void scan_targets(const EmdSmem &S, int k0, int k1, float ax, float ay, float az, Top2 &r) {
-    int k = k0;
+// One tile of 32 targets for the bidder at (ax,ay,az).  e = u*u - s with u = c_k - tm: e < 0 proves
+// value_k < (final second best), so the candidate cannot change best / second best / argmax.
+__device__ __forceinline__ void scan_tile(const EmdSmem &S, int k0, float ax, float ay, float az, Top2 &r) {
 #define PCL_FILTER(T_, S_, E_)                                                                   \
     const float4 T_ = S.tgt[k_];                                                                 \
     const float S_ = sq3_ref(__fsub_rn(T_.x, ax), __fsub_rn(T_.y, ay), __fsub_rn(T_.z, az));     \
     const float u_##E_ = __fsub_rn(T_.w, r.tm);                                                   \
     const float E_ = __fmaf_rn(u_##E_, u_##E_, -S_);
-    for (; k + 4 <= k1; k += 4) {
+#pragma unroll 2
+    for (int k = k0; k < k0 + TILE; k += 4) {
         float e0, e1, e2, e3, s0, s1, s2, s3;
         { const int k_ = k;     PCL_FILTER(t, s, e) e0 = e; s0 = s; }
         { const int k_ = k + 1; PCL_FILTER(t, s, e) e1 = e; s1 = s; }
         { const int k_ = k + 2; PCL_FILTER(t, s, e) e2 = e; s2 = s; }
         { const int k_ = k + 3; PCL_FILTER(t, s, e) e3 = e; s3 = s; }
         if (!(fmaxf(fmaxf(e0, e1), fmaxf(e2, e3)) < 0.f)) {  // rare: some candidate may be in the top 2
-            r.n_slowgrp++;
-            if (!(e0 < 0.f)) top2_exact(r, s0, S.pf[k], k);
-            if (!(e1 < 0.f)) top2_exact(r, s1, S.pf[k + 1], k + 1);
-            if (!(e2 < 0.f)) top2_exact(r, s2, S.pf[k + 2], k + 2);
-            if (!(e3 < 0.f)) top2_exact(r, s3, S.pf[k + 3], k + 3);
+            if (!(e0 < 0.f)) top2_exact(S, r, s0, k);
+            if (!(e1 < 0.f)) top2_exact(S, r, s1, k + 1);
+            if (!(e2 < 0.f)) top2_exact(S, r, s2, k + 2);
+            if (!(e3 < 0.f)) top2_exact(S, r, s3, k + 3);
         }
     }
-    for (; k < k1; k++) {
-        const int k_ = k;
-        PCL_FILTER(t, s, e)
-        if (!(e < 0.f)) top2_exact(r, s, S.pf[k], k);
-    }
 #undef PCL_FILTER
+}
+
+// Can the whole tile be skipped for this bidder?  Lower bound of s over the tile = squared distance to the
+// tile's box (shrunk by 1e-6 relative against fp32 rounding of both sides), upper bound of c = tile max.
+__device__ __forceinline__ bool tile_skippable(const float4 &lo, const float4 &hi, float ax, float ay, float az, float tm) {
+    const float dx = fmaxf(fmaxf(__fsub_rn(lo.x, ax), __fsub_rn(ax, hi.x)), 0.f);
+    const float dy = fmaxf(fmaxf(__fsub_rn(lo.y, ay), __fsub_rn(ay, hi.y)), 0.f);
+    const float dz = fmaxf(fmaxf(__fsub_rn(lo.z, az), __fsub_rn(az, hi.z)), 0.f);
+    const float d2 = __fmul_rn(__fmaf_rn(dz, dz, __fmaf_rn(dx, dx, __fmul_rn(dy, dy))), 0.999999f);
+    const float u = __fsub_rn(lo.w, tm);
+    return (u < 0.f) || (__fmaf_rn(u, u, -d2) < 0.f);
 }
 
 // Start of a scan: seed the threshold with the exact current values of the two objects this bidder
 // preferred last time (their prices may have risen since; any two distinct objects give a valid bound).
 __device__ __forceinline__ Top2 top2_init(const EmdSmem &S, unsigned lastpack, int N, float ax, float ay, float az) {
     Top2 r;
-    r.best = -1e9f; r.better = -1e9f; r.bi = -1; r.bi2 = -1; r.tm = -1e9f; r.n_exact = 0; r.n_slowgrp = 0;
+    r.best = -1e9f; r.better = -1e9f; r.bi = -1; r.bi2 = -1; r.bio = 0x7fffffff; r.tm = -1e9f;
     const int k1 = (int)(lastpack & 0xffffu), k2 = (int)(lastpack >> 16);
     if (lastpack != NOLAST && k1 < N && k2 < N && k1 != k2) {
         const float4 t1 = S.tgt[k1], t2 = S.tgt[k2];
@@ -165,7 +217,7 @@ __device__ __forceinline__ Top2 top2_init(const EmdSmem &S, unsigned lastpack, i
 // reached through the PCL_EMD_PROFILE environment variable; the product path instantiates PROF=false).
 template <bool PROF>
 __global__ void __launch_bounds__(EMD_THREADS, 1)
-emd_auction_kernel(Pts xyz1, Pts xyz2, int N, float eps, int iters, int x1_smem, float *__restrict__ dist,
+emd_auction_kernel(Pts xyz1, Pts xyz2, int N, float eps, int iters, int flags, int pcap, float *__restrict__ dist,
                    int *__restrict__ assignment, int *__restrict__ stats, long long *__restrict__ prof) {
     long long pt[8] = {0, 0, 0, 0, 0, 0, 0, 0}, pc = 0;
 #define PCL_TICK(i)                                              \
@@ -179,20 +231,40 @@ emd_auction_kernel(Pts xyz1, Pts xyz2, int N, float eps, int iters, int x1_smem,
     cg::cluster_group cluster = cg::this_cluster();
     const int cs = (int)cluster.num_blocks(), rank = (int)cluster.block_rank();
     const int cloud = blockIdx.x / cs;
-    const int tid = threadIdx.x, T = EMD_THREADS;
-    const EmdSmem S = carve(smem_raw, N, x1_smem != 0);
-    const int n8 = (N + 7) / 8 * 8;
+    const int tid = threadIdx.x, T = EMD_THREADS, lane = tid & 31, wid = tid >> 5;
+    const EmdSmem S = carve(smem_raw, N, flags, pcap);
+    int *const work_ctr = S.wsum + 24;  // dynamic work-item counter of the bid phase (wsum[0..15] = warp sums)
+    const int n8 = (N + 7) / 8 * 8, n32 = (N + 31) / 32 * 32, NT = n32 / TILE;
 
-    // ---- init (emd_module.py:45-56) --------------------------------------------------------------
-    for (int j = tid; j < n8; j += T) {
-        if (j < N) {
-            const float3 p = ld_xyz(xyz2, cloud, j);
-            S.tgt[j] = make_float4(p.x, p.y, p.z, 3.0f);
-            if (x1_smem) {
-                const float3 q = ld_xyz(xyz1, cloud, j);
-                S.x1[j] = make_float4(q.x, q.y, q.z, 0.f);
+    // ---- init: internal (Morton) order of both clouds, tiles, auction state (emd_module.py:45-56) ----------
+    if (tid == 0) *S.evals = 0ull;
+    if (flags & EMD_F_SORT) {
+        unsigned *keys = reinterpret_cast<unsigned *>(S.pub);  // 16N bytes of scratch >= 4 * np
+        int np = 1;
+        while (np < N) np <<= 1;
+        for (int pass = 0; pass < 2; pass++) {  // 0: targets, 1: predictions
+            const Pts &src = pass ? xyz1 : xyz2;
+            for (int k = tid; k < np; k += T)
+                keys[k] = (k < N) ? ((morton18(ld_xyz(src, cloud, k)) << 12) | (unsigned)k) : 0xffffffffu;
+            __syncthreads();
+            bitonic_sort(keys, np);
+            for (int k = tid; k < N; k += T) {
+                const int orig = (int)(keys[k] & 0xfffu);
+                const float3 p = ld_xyz(src, cloud, orig);
+                if (pass == 0) { S.tperm[k] = (unsigned short)orig; S.tgt[k] = make_float4(p.x, p.y, p.z, 3.0f); }
+                else { S.pperm[k] = (unsigned short)orig; if (S.x1) S.x1[k] = make_float4(p.x, p.y, p.z, 0.f); }
             }
+            __syncthreads();
         }
+    } else {
+        for (int k = tid; k < N; k += T) {
+            const float3 p = ld_xyz(xyz2, cloud, k);
+            S.tgt[k] = make_float4(p.x, p.y, p.z, 3.0f);
+            if (S.x1) { const float3 q = ld_xyz(xyz1, cloud, k); S.x1[k] = make_float4(q.x, q.y, q.z, 0.f); }
+        }
+    }
+    for (int k = N + tid; k < n32; k += T) S.tgt[k] = make_float4(1e18f, 1e18f, 1e18f, -1e30f);  // never a candidate
+    for (int j = tid; j < n8; j += T) {
         S.pf[j] = 0.f;
         S.asg[j] = (j < N) ? NONE16 : (unsigned short)0;
         S.inv[j] = NONE16;
@@ -200,21 +272,45 @@ emd_auction_kernel(Pts xyz1, Pts xyz2, int N, float eps, int iters, int x1_smem,
         S.maxidx[j] = -1;
         S.last[j] = NOLAST;
     }
+    __syncthreads();
+    for (int t = wid; t < NT; t += EMD_WARPS) {  // tile boxes
+        const int k = t * TILE + lane;
+        const float4 p = S.tgt[k];
+        const bool ok = k < N;
+        float lx = ok ? p.x : 3e38f, ly = ok ? p.y : 3e38f, lz = ok ? p.z : 3e38f;
+        float hx = ok ? p.x : -3e38f, hy = ok ? p.y : -3e38f, hz = ok ? p.z : -3e38f;
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) {
+            lx = fminf(lx, __shfl_xor_sync(0xffffffffu, lx, o)); ly = fminf(ly, __shfl_xor_sync(0xffffffffu, ly, o));
+            lz = fminf(lz, __shfl_xor_sync(0xffffffffu, lz, o)); hx = fmaxf(hx, __shfl_xor_sync(0xffffffffu, hx, o));
+            hy = fmaxf(hy, __shfl_xor_sync(0xffffffffu, hy, o)); hz = fmaxf(hz, __shfl_xor_sync(0xffffffffu, hz, o));
+        }
+        if (lane == 0) { S.tlo[t] = make_float4(lx, ly, lz, 3.0f); S.thi[t] = make_float4(hx, hy, hz, 0.f); }
+    }
     cluster.sync();  // every CTA's arrays exist before anyone writes remote bids
     PCL_TICK(0)
 
-    auto pred_xyz = [&](int j) -> float3 {
-        if (x1_smem) { const float4 q = S.x1[j]; return make_float3(q.x, q.y, q.z); }
-        return ld_xyz(xyz1, cloud, j);
+    auto pred_xyz = [&](int jp) -> float3 {
+        if (S.x1) { const float4 q = S.x1[jp]; return make_float3(q.x, q.y, q.z); }
+        return ld_xyz(xyz1, cloud, S.pperm ? (int)S.pperm[jp] : jp);
     };
     long long sum_u = 0;
+    unsigned long long my_evals = 0ull;  // evaluations this lane really executed (tiles that were not skipped)
     int iters_run = 0, extra_qualifiers = 0, cur = 0;
     const int E = (n8 / 8 + T - 1) / T * 8;  // contiguous elements per thread in the compaction (multiple of 8, <= 32)
 
     for (int t = 0; t < iters; t++) {
         const bool last = (t == iters - 1);
         // ---- 1. list of unassigned bidders (emd_cuda.cu:23-93), ascending, identical in every CTA -------
-        unsigned flags = 0;
+        if (t > 0) {  // prices moved in the previous iteration: refresh the per-tile upper bound of c (same barrier interval)
+            for (int tl = wid; tl < NT; tl += EMD_WARPS) {
+                float c = S.tgt[tl * TILE + lane].w;
+#pragma unroll
+                for (int o = 16; o > 0; o >>= 1) c = fmaxf(c, __shfl_xor_sync(0xffffffffu, c, o));
+                if (lane == 0) S.tlo[tl].w = c;
+            }
+        }
+        unsigned fl = 0;
         {
             const int base = tid * E;
             for (int e = 0; e < E; e += 8) {
@@ -223,35 +319,36 @@ emd_auction_kernel(Pts xyz1, Pts xyz2, int N, float eps, int iters, int x1_smem,
                     const unsigned w[4] = {a.x, a.y, a.z, a.w};
 #pragma unroll
                     for (int h = 0; h < 4; h++) {
-                        flags |= (unsigned)((w[h] & 0xffffu) == NONE16) << (e + 2 * h);
-                        flags |= (unsigned)((w[h] >> 16) == NONE16) << (e + 2 * h + 1);
+                        fl |= (unsigned)((w[h] & 0xffffu) == NONE16) << (e + 2 * h);
+                        fl |= (unsigned)((w[h] >> 16) == NONE16) << (e + 2 * h + 1);
                     }
                 }
             }
         }
-        const int cnt = __popc(flags);
+        const int cnt = __popc(fl);
         int incl = cnt;
 #pragma unroll
         for (int o = 1; o < 32; o <<= 1) {
             const int v = __shfl_up_sync(0xffffffffu, incl, o);
-            if ((tid & 31) >= o) incl += v;
+            if (lane >= o) incl += v;
         }
-        if ((tid & 31) == 31) S.wsum[tid >> 5] = incl;
+        if (lane == 31) S.wsum[wid] = incl;
         __syncthreads();
         int wbase = 0, U = 0;
 #pragma unroll
-        for (int w = 0; w < T / 32; w++) {
+        for (int w = 0; w < EMD_WARPS; w++) {
             const int v = S.wsum[w];
-            if (w < (tid >> 5)) wbase += v;
+            if (w < wid) wbase += v;
             U += v;
         }
         if (U == 0) break;  // uniform across the cluster: replicas are identical
+        if (tid == 0) *work_ctr = 0;
         {
             int pos = wbase + incl - cnt;
             const int base = tid * E;
-            while (flags) {
-                const int e = __ffs(flags) - 1;
-                flags &= flags - 1;
+            while (fl) {
+                const int e = __ffs(fl) - 1;
+                fl &= fl - 1;
                 S.unass[pos++] = (unsigned short)(base + e);
             }
         }
@@ -261,123 +358,214 @@ emd_auction_kernel(Pts xyz1, Pts xyz2, int N, float eps, int iters, int x1_smem,
         PCL_TICK(1)
 
         // ---- 2. Bid (emd_cuda.cu:95-179) for this CTA's share of the bidders ----------------------------
-        const int per = (U + cs - 1) / cs;
-        const int lo = rank * per;
-        const int Uc = max(0, min(U, lo + per) - lo);
-        int KC = 1;
-        if (Uc > 0 && Uc < T) KC = max(1, min(T / Uc, N / 32));
+        // A warp owns 32 consecutive (= spatially close) bidders and one interleaved slice of the target tiles;
+        // a tile is skipped when every lane proves that none of its 32 targets can reach the lane's top 2.
+        // The (spatially sorted) list is dealt to the CTAs of the cluster in an interleaved way -- single bidders when
+        // there are few (warp-per-bidder mode), blocks of 32 neighbours otherwise -- so that every CTA sees the
+        // same mix of easy and hard regions.  list position of local bidder b:  pos(b).
+        const bool wpb = (U > 0 && (U + cs - 1) / cs <= EMD_WPB_MAX);
+        const int gsz = wpb ? 1 : 32;                       // dealing granularity
+        const int nblk = (U + gsz - 1) / gsz;               // blocks in the list
+        const int myblk = (nblk > rank) ? (nblk - rank + cs - 1) / cs : 0;  // blocks rank, rank+cs, ...
+        int Uc = myblk * gsz;
+        if (myblk > 0 && (rank + (myblk - 1) * cs) == nblk - 1) Uc -= nblk * gsz - U;  // the last block may be short
+        auto pos = [&](int b) -> int { return ((b / gsz) * cs + rank) * gsz + (b % gsz); };
+        const int Gn = (Uc + 31) >> 5;                                   // bidder groups (warps' worth)
+        // tile slices per group: aim at ~4 work items per warp (dynamic queue), bounded by the partial buffer
+        int KS = 1;
+        if (Gn > 0 && Gn < 4 * EMD_WARPS) KS = max(1, min(min((4 * EMD_WARPS + Gn - 1) / Gn, NT), pcap / (Gn * 32)));
+        const int GS = Gn * 32;                                          // partial stride of one slice
         uint2 *pub_cur = S.pub + cur * n8;
 
-        auto publish = [&](int j, const Top2 &r) {
-            const float inc = __fadd_rn(__fsub_rn(r.best, r.better), eps);  // emd_cuda.cu:175
-            const uint2 v = make_uint2((unsigned)(r.bi & 0xffff) | ((unsigned)(r.bi2 & 0xffff) << 16), __float_as_uint(inc));
-            for (int c = 0; c < cs; c++) cluster.map_shared_rank(pub_cur, c)[j] = v;
+        auto publish = [&](int jp, float best, float better, unsigned pack) {
+            const float inc = __fadd_rn(__fsub_rn(best, better), eps);  // emd_cuda.cu:175
+            const uint2 v = make_uint2(pack, __float_as_uint(inc));
+            for (int c = 0; c < cs; c++) cluster.map_shared_rank(pub_cur, c)[jp] = v;
         };
 
-        if (KC == 1) {
-            for (int b0 = 0; b0 < Uc; b0 += T) {
-                const int b = b0 + tid;
-                if (b < Uc) {
-                    const int j = S.unass[lo + b];
-                    const float3 a = pred_xyz(j);
-                    Top2 r = top2_init(S, S.last[j], N, a.x, a.y, a.z);
-                    scan_targets(S, 0, N, a.x, a.y, a.z, r);
-                    publish(j, r);
-                }
-            }
-        } else {
-            const int items = Uc * KC;  // <= T
-            long long ts[5] = {0, 0, 0, 0, 0};
-            if (tid < items) {
-                const int c = tid / Uc, b = tid - c * Uc;
-                const int j = S.unass[lo + b];
-                const float3 a = pred_xyz(j);
-                if constexpr (PROF) { ts[0] = clock64() + (long long)(a.x * 0.f); }
-                Top2 r = top2_init(S, S.last[j], N, a.x, a.y, a.z);
-                if constexpr (PROF) { ts[1] = clock64() + (long long)(r.tm * 0.f); }
-                const int k0 = (int)(((long long)c * N) / KC), k1 = (int)(((long long)(c + 1) * N) / KC);
-                scan_targets(S, k0, k1, a.x, a.y, a.z, r);
-                if constexpr (PROF) { ts[2] = clock64() + (long long)(r.best * 0.f); }
-                S.pbest[tid] = r.best; S.pbetter[tid] = r.better;
-                S.pbi[tid] = (unsigned)(r.bi & 0xffff) | ((unsigned)(r.bi2 & 0xffff) << 16);
-            }
-            __syncthreads();
-            if constexpr (PROF) {
-                ts[3] = clock64();
-                if (blockIdx.x == 0 && tid == 0 && prof && t < 50)
-                    for (int i = 0; i < 4; i++) prof[(size_t)gridDim.x * 8 + 128 + t * 4 + i] = ts[i] - pc;
-            }
-            // Tree merge of the KC chunk partials of every bidder (log2 KC steps).  Equivalent to the reference's
-            // sequential merge in ascending k (emd_cuda.cu:165-173): best = max, its index = the LOWEST k among
-            // equal maxima (explicit index compare makes the merge order-independent), better = second largest
-            // counting duplicates.
-            {
-                const int c = tid / Uc, b = tid - c * Uc;
-                int span = 1;
-                while (span < KC) span <<= 1;
-                for (int st = span >> 1; st >= 1; st >>= 1) {
-                    if (tid < items && c < st && c + st < KC) {
-                        const int me = c * Uc + b, ot = (c + st) * Uc + b;
-                        float best = S.pbest[me], better = S.pbetter[me];
-                        unsigned pk = S.pbi[me];
-                        const float ob = S.pbest[ot], obt = S.pbetter[ot];
-                        const unsigned opk = S.pbi[ot];
-                        const bool other_wins = (ob > best) || (ob == best && (opk & 0xffffu) < (pk & 0xffffu));
-                        if (other_wins) {
-                            // new second best = max(old best, other's second best)
-                            const unsigned second = (best >= obt) ? (pk & 0xffffu) : (opk >> 16);
-                            better = fmaxf(best, obt);
-                            best = ob;
-                            pk = (opk & 0xffffu) | (second << 16);
-                        } else if (ob > better) {
-                            better = ob;
-                            pk = (pk & 0xffffu) | ((opk & 0xffffu) << 16);
+        if (wpb) {
+            // ---- few bidders: one WARP per bidder, one lane per target of a tile.  The tile tests are exact per
+            // bidder (no other lane's neighbourhood keeps a tile alive), 32 boxes are tested per ballot, and the
+            // rare candidates are folded into a warp-uniform top 2 in any order (the update is order-independent).
+            for (;;) {
+                int b = 0;
+                if (lane == 0) b = atomicAdd(work_ctr, 1);
+                b = __shfl_sync(0xffffffffu, b, 0);
+                if (b >= Uc) break;
+                const int jp = S.unass[pos(b)];
+                const float3 a = pred_xyz(jp);
+                const unsigned lp = S.last[jp];
+                float tm = -1e9f;
+                {
+                    const int k1 = (int)(lp & 0xffffu), k2 = (int)(lp >> 16);
+                    if (lp != NOLAST && k1 < N && k2 < N && k1 != k2) {  // seeds: lanes 0 and 1 evaluate them in parallel
+                        float v = 0.f;
+                        if (lane < 2) {
+                            const int ks = lane ? k2 : k1;
+                            const float4 tq = S.tgt[ks];
+                            v = bid_value_exact(sq3_ref(__fsub_rn(tq.x, a.x), __fsub_rn(tq.y, a.y), __fsub_rn(tq.z, a.z)), S.pf[ks]);
                         }
-                        S.pbest[me] = best; S.pbetter[me] = better; S.pbi[me] = pk;
+                        tm = __fsub_rn(fminf(__shfl_sync(0xffffffffu, v, 0), __shfl_sync(0xffffffffu, v, 1)), FILTER_MARGIN);
                     }
-                    __syncthreads();
                 }
-                if (tid < Uc) {
-                    Top2 r;
-                    r.best = S.pbest[tid]; r.better = S.pbetter[tid];
-                    r.bi = (int)(S.pbi[tid] & 0xffffu); r.bi2 = (int)(S.pbi[tid] >> 16); r.tm = 0.f;
-                    publish(S.unass[lo + tid], r);
+                float best = -1e9f, better = -1e9f;
+                int bi = -1, bi2 = -1, bio = 0x7fffffff;
+                for (int tb = 0; tb < NT; tb += 32) {
+                    const int tl = tb + lane;
+                    bool cand = false;
+                    if (tl < NT) cand = !tile_skippable(S.tlo[tl], S.thi[tl], a.x, a.y, a.z, tm);
+                    unsigned cm = __ballot_sync(0xffffffffu, cand);
+                    while (cm) {  // up to 4 candidate tiles per step: 4 independent filter chains per lane, one vote
+                        int tix[4];
+                        bool have[4];
+#pragma unroll
+                        for (int i = 0; i < 4; i++) {
+                            have[i] = cm != 0;
+                            tix[i] = tb + (have[i] ? __ffs(cm) - 1 : 0);
+                            cm &= cm - 1;  // cm == 0 stays 0
+                        }
+                        float sq[4];
+                        bool pass[4];
+                        bool any = false;
+#pragma unroll
+                        for (int i = 0; i < 4; i++) {
+                            const float4 tq = S.tgt[tix[i] * TILE + lane];
+                            sq[i] = sq3_ref(__fsub_rn(tq.x, a.x), __fsub_rn(tq.y, a.y), __fsub_rn(tq.z, a.z));
+                            const float u = __fsub_rn(tq.w, tm);
+                            pass[i] = have[i] && !(__fmaf_rn(u, u, -sq[i]) < 0.f);
+                            any |= pass[i];
+                        }
+                        if (lane == 0) my_evals += TILE * ((int)have[0] + (int)have[1] + (int)have[2] + (int)have[3]);
+                        if (!__any_sync(0xffffffffu, any)) continue;
+#pragma unroll
+                        for (int i = 0; i < 4; i++) {
+                            unsigned pm = __ballot_sync(0xffffffffu, pass[i]);
+                            if (!pm) continue;
+                            const int k = tix[i] * TILE + lane;
+                            float v = 0.f;
+                            int ko = 0;
+                            if (pass[i]) { v = bid_value_exact(sq[i], S.pf[k]); ko = S.tperm ? (int)S.tperm[k] : k; }
+                            while (pm) {
+                                const int l = __ffs(pm) - 1;
+                                pm &= pm - 1;
+                                const float vl = __shfl_sync(0xffffffffu, v, l);
+                                const int kol = __shfl_sync(0xffffffffu, ko, l), kl = tix[i] * TILE + l;
+                                if (vl > best || (vl == best && kol < bio)) { better = best; bi2 = bi; best = vl; bi = kl; bio = kol; }
+                                else if (vl > better) { better = vl; bi2 = kl; }
+                            }
+                        }
+                        tm = fmaxf(tm, __fsub_rn(better, FILTER_MARGIN));
+                    }
                 }
+                if (lane == 0) publish(jp, best, better, (unsigned)(bi & 0xffff) | ((unsigned)(bi2 & 0xffff) << 16));
+            }
+        } else
+        for (;;) {
+            int it = 0;
+            if (lane == 0) it = atomicAdd(work_ctr, 1);
+            it = __shfl_sync(0xffffffffu, it, 0);
+            if (it >= Gn * KS) break;
+            const int g = it % Gn, sl = it / Gn;
+            const int b = min(g * 32 + lane, Uc - 1);          // surplus lanes shadow the last bidder (results discarded)
+            const bool active = (g * 32 + lane) < Uc;
+            const int jp = S.unass[pos(b)];
+            const float3 a = pred_xyz(jp);
+            Top2 r = top2_init(S, S.last[jp], N, a.x, a.y, a.z);
+            const int ntl = (NT - sl + KS - 1) / KS;           // tiles of this slice: sl, sl+KS, ...
+            const int home = min(max((__shfl_sync(0xffffffffu, jp, 0) / TILE - sl + KS / 2) / KS, 0), ntl - 1);
+            for (int m = 0; m < ntl; m++) {                    // zig-zag outwards from the tile next to the bidders
+                int q = home + ((m & 1) ? ((m + 1) >> 1) : -(m >> 1));
+                q += (q < 0) ? ntl : 0;
+                q -= (q >= ntl) ? ntl : 0;
+                const int tl = sl + q * KS;
+                if (__all_sync(0xffffffffu, tile_skippable(S.tlo[tl], S.thi[tl], a.x, a.y, a.z, r.tm))) continue;
+                scan_tile(S, tl * TILE, a.x, a.y, a.z, r);
+                my_evals += active ? TILE : 0;
+            }
+            const unsigned pack = (unsigned)(r.bi & 0xffff) | ((unsigned)(r.bi2 & 0xffff) << 16);
+            if (KS == 1) {
+                if (active) publish(jp, r.best, r.better, pack);
+            } else if (active) {
+                S.pbest[sl * GS + b] = r.best; S.pbetter[sl * GS + b] = r.better; S.pbi[sl * GS + b] = pack;
             }
         }
+        if (!wpb && KS > 1) {
+            __syncthreads();
+            // Tree merge of the KS slice partials of every bidder (log2 KS steps); same order-independent rule as
+            // top2_exact, i.e. the reference's ascending merge (emd_cuda.cu:165-173).
+            int span = 1;
+            while (span < KS) span <<= 1;
+            for (int st = span >> 1; st >= 1; st >>= 1) {
+                const int rows = min(st, KS - st);  // slices c in [0, rows) absorb slice c + st
+                for (int idx = tid; idx < rows * Uc; idx += T) {
+                    const int c = idx / Uc, b = idx - c * Uc;
+                    const int me = c * GS + b, ot = (c + st) * GS + b;
+                    float best = S.pbest[me], better = S.pbetter[me];
+                    unsigned pk = S.pbi[me];
+                    const float ob = S.pbest[ot], obt = S.pbetter[ot];
+                    const unsigned opk = S.pbi[ot];
+                    bool other_wins = ob > best;
+                    if (ob == best && (opk & 0xffffu) != 0xffffu) {
+                        const unsigned mine = pk & 0xffffu;
+                        if (mine == 0xffffu) other_wins = true;
+                        else {
+                            const unsigned mo = S.tperm ? S.tperm[mine] : mine, oo = S.tperm ? S.tperm[opk & 0xffffu] : (opk & 0xffffu);
+                            other_wins = oo < mo;
+                        }
+                    }
+                    if (other_wins) {
+                        const unsigned second = (best >= obt) ? (pk & 0xffffu) : (opk >> 16);
+                        better = fmaxf(best, obt);
+                        best = ob;
+                        pk = (opk & 0xffffu) | (second << 16);
+                    } else if (ob > better) {
+                        better = ob;
+                        pk = (pk & 0xffffu) | ((opk & 0xffffu) << 16);
+                    }
+                    S.pbest[me] = best; S.pbetter[me] = better; S.pbi[me] = pk;
+                }
+                __syncthreads();
+            }
+            for (int b = tid; b < Uc; b += T) publish(S.unass[pos(b)], S.pbest[b], S.pbetter[b], S.pbi[b]);
+        }
         if constexpr (PROF) {
-            if (blockIdx.x == 0 && tid == 0 && prof && t < 64) {
-                prof[(size_t)gridDim.x * 8 + t * 2] = U;
-                prof[(size_t)gridDim.x * 8 + t * 2 + 1] = clock64() - pc;
+            if (blockIdx.x == 0 && tid == 0 && prof && t < 50) {
+                prof[(size_t)gridDim.x * 8 + t * 4] = U;
+                prof[(size_t)gridDim.x * 8 + t * 4 + 1] = clock64() - pc;
+                prof[(size_t)gridDim.x * 8 + t * 4 + 2] = KS * 1000 + Gn;
             }
         }
         PCL_TICK(2)
         cluster.sync();  // all bids of this iteration are visible in every CTA
+        if constexpr (PROF) {
+            if (blockIdx.x == 0 && tid == 0 && prof && t < 50) prof[(size_t)gridDim.x * 8 + t * 4 + 3] = clock64() - pc;
+        }
         PCL_TICK(3)
 
         // ---- 3. GetMax + Assign (emd_cuda.cu:181-215), replicated in every CTA -------------------------
         for (int q = tid; q < U; q += T) {
-            const int j = S.unass[q];
-            const uint2 pb = pub_cur[j];
-            S.last[j] = pb.x;
+            const int jp = S.unass[q];
+            const uint2 pb = pub_cur[jp];
+            S.last[jp] = pb.x;
             atomic_max_float(&S.maxinc[pb.x & 0xffffu], __uint_as_float(pb.y));  // emd_cuda.cu:176
         }
         __syncthreads();
         for (int q = tid; q < U; q += T) {
-            const int j = S.unass[q];
-            const uint2 pb = pub_cur[j];
+            const int jp = S.unass[q];
+            const uint2 pb = pub_cur[jp];
             const int o = (int)(pb.x & 0xffffu);
             const double bi = (double)__uint_as_float(pb.y), mi = (double)S.maxinc[o];
-            if (bi - 1e-6 <= mi && mi <= bi + 1e-6) atomicMax(&S.maxidx[o], j);  // :188-191, largest j wins
+            if (bi - 1e-6 <= mi && mi <= bi + 1e-6)  // :188-191; the largest ORIGINAL bidder index wins
+                atomicMax(&S.maxidx[o], S.pperm ? (int)S.pperm[jp] : jp);
         }
         __syncthreads();
         // decisions are all taken before any state is modified (U <= 4096 => at most 8 passes per thread)
         unsigned winmask = 0;
         for (int q = tid, p = 0; q < U; q += T, p++) {
-            const int j = S.unass[q];
-            const uint2 pb = pub_cur[j];
+            const int jp = S.unass[q];
+            const uint2 pb = pub_cur[jp];
             const int o = (int)(pb.x & 0xffffu);
-            const bool winner = (S.maxidx[o] == j);
+            const bool winner = (S.maxidx[o] == (S.pperm ? (int)S.pperm[jp] : jp));
             if (last || winner) winmask |= 1u << p;  // emd_cuda.cu:201
             if (!winner && rank == 0) {               // statistics only: bidders inside the window that lost the race
                 const double bi = (double)__uint_as_float(pb.y), mi = (double)S.maxinc[o];
@@ -387,13 +575,13 @@ emd_auction_kernel(Pts xyz1, Pts xyz2, int N, float eps, int iters, int x1_smem,
         __syncthreads();
         for (int q = tid, p = 0; q < U; q += T, p++) {
             if (!((winmask >> p) & 1u)) continue;
-            const int j = S.unass[q];
-            const uint2 pb = pub_cur[j];
+            const int jp = S.unass[q];
+            const uint2 pb = pub_cur[jp];
             const int o = (int)(pb.x & 0xffffu);  // emd_cuda.cu:203-211
             const unsigned prev = S.inv[o];
             if (!last && prev != NONE16) S.asg[prev] = NONE16;
-            S.inv[o] = (unsigned short)j;
-            S.asg[j] = (unsigned short)o;
+            S.inv[o] = (unsigned short)jp;
+            S.asg[jp] = (unsigned short)o;
             const float pnew = __fadd_rn(S.pf[o], __uint_as_float(pb.y));
             S.pf[o] = pnew;
             S.tgt[o].w = __fsub_ru(3.0f, pnew);  // c = RU(3 - price): upper bound used by the filter
@@ -405,18 +593,19 @@ emd_auction_kernel(Pts xyz1, Pts xyz2, int N, float eps, int iters, int x1_smem,
         PCL_TICK(4)
     }
 
-    // ---- CalcDist (emd_cuda.cu:217-226) + outputs; the cloud's points are split over the cluster ---------
+    // ---- CalcDist (emd_cuda.cu:217-226) + outputs in ORIGINAL index order; points split over the cluster ----
     __syncthreads();
-    for (int j = rank * T + tid; j < N; j += cs * T) {
-        const unsigned k = S.asg[j];
+    for (int jp = rank * T + tid; jp < N; jp += cs * T) {
+        const unsigned k = S.asg[jp];
         float d = 0.f;
         if (k != NONE16) {
-            const float3 a = pred_xyz(j);
+            const float3 a = pred_xyz(jp);
             const float4 tp = S.tgt[k];
             d = sq3_ref(__fsub_rn(a.x, tp.x), __fsub_rn(a.y, tp.y), __fsub_rn(a.z, tp.z));
         }
-        dist[(size_t)cloud * N + j] = d;
-        assignment[(size_t)cloud * N + j] = (k != NONE16) ? (int)k : -1;
+        const int jo = S.pperm ? (int)S.pperm[jp] : jp;
+        dist[(size_t)cloud * N + jo] = d;
+        assignment[(size_t)cloud * N + jo] = (k != NONE16) ? (S.tperm ? (int)S.tperm[k] : (int)k) : -1;
     }
     PCL_TICK(5)
     if constexpr (PROF) {
@@ -424,18 +613,25 @@ emd_auction_kernel(Pts xyz1, Pts xyz2, int N, float eps, int iters, int x1_smem,
             for (int i = 0; i < 8; i++) prof[(size_t)blockIdx.x * 8 + i] = pt[i];
     }
 #undef PCL_TICK
-    if (stats && rank == 0) {
+    if (stats) {  // uniform over the grid
 #pragma unroll
-        for (int o = 16; o > 0; o >>= 1) extra_qualifiers += __shfl_xor_sync(0xffffffffu, extra_qualifiers, o);
-        if ((tid & 31) == 0) S.wsum[tid >> 5] = extra_qualifiers;
-        __syncthreads();
-        if (tid == 0) {
+        for (int o = 16; o > 0; o >>= 1) {
+            extra_qualifiers += __shfl_xor_sync(0xffffffffu, extra_qualifiers, o);
+            my_evals += __shfl_xor_sync(0xffffffffu, my_evals, o);
+        }
+        if (lane == 0) {
+            atomicAdd(cluster.map_shared_rank(S.evals, 0), my_evals);
+            S.wsum[wid] = extra_qualifiers;
+        }
+        cluster.sync();
+        if (rank == 0 && tid == 0) {
             int e = 0;
-            for (int w = 0; w < T / 32; w++) e += S.wsum[w];
-            stats[cloud * 4 + 0] = (int)sum_u;
-            stats[cloud * 4 + 1] = iters_run;
-            stats[cloud * 4 + 2] = e;
-            stats[cloud * 4 + 3] = cs;
+            for (int w = 0; w < EMD_WARPS; w++) e += S.wsum[w];
+            int *st = stats + (size_t)cloud * 8;
+            st[0] = (int)sum_u; st[1] = iters_run; st[2] = e; st[3] = cs;
+            const unsigned long long ce = *S.evals;
+            st[4] = (int)(ce & 0xffffffffull); st[5] = (int)(ce >> 32);
+            st[6] = flags; st[7] = NT;
         }
     }
 }
@@ -588,8 +784,13 @@ extern "C" int pcl_emd_fwd(const void *xyz1, int dtype1, int64_t bs1, int64_t rs
     cudaStream_t st = (cudaStream_t)stream;
     DeviceInfo di;
     if ((rc = device_info(&di))) return rc;
-    const bool with_x1 = emd_smem_bytes(N, true) <= (size_t)di.max_smem_optin;
-    const size_t smem = emd_smem_bytes(N, with_x1);
+    int flags = 0;
+    if (emd_smem_bytes(N, EMD_F_SORT) <= (size_t)di.max_smem_optin) flags |= EMD_F_SORT;
+    if (emd_smem_bytes(N, flags | EMD_F_X1) <= (size_t)di.max_smem_optin) flags |= EMD_F_X1;
+    if (getenv("PCL_EMD_NO_SORT")) flags &= ~EMD_F_SORT;  // development aid: natural order (no spatial pruning benefit)
+    int pcap = 4 * EMD_THREADS;  // room for 64 work items with partials; fall back to 16 when shared memory is tight
+    if (emd_smem_bytes(N, flags, pcap) > (size_t)di.max_smem_optin) pcap = EMD_THREADS;
+    const size_t smem = emd_smem_bytes(N, flags, pcap);
     if (smem > (size_t)di.max_smem_optin) { set_error("emd_fwd: N=%d needs %zu B shared memory (> %d)", N, smem, di.max_smem_optin); return PCL_E_UNSUPPORTED; }
     static thread_local int attr_dev = -1;
     int dev = 0;
@@ -612,9 +813,9 @@ extern "C" int pcl_emd_fwd(const void *xyz1, int dtype1, int64_t bs1, int64_t rs
     // development aid: PCL_EMD_PROFILE=1 makes the workspace receive per-phase clock totals (B*cs*8 int64)
     static const bool profile = getenv("PCL_EMD_PROFILE") != nullptr;
     if (profile && workspace && workspace_bytes >= ((size_t)B * cs * 8 + 512) * sizeof(long long)) {
-        PCL_CUDA(cudaLaunchKernelEx(&cfg, emd_auction_kernel<true>, p1, p2, N, eps, iters, (int)with_x1, dist, (int *)assignment, (int *)stats, (long long *)workspace));
+        PCL_CUDA(cudaLaunchKernelEx(&cfg, emd_auction_kernel<true>, p1, p2, N, eps, iters, flags, pcap, dist, (int *)assignment, (int *)stats, (long long *)workspace));
     } else {
-        PCL_CUDA(cudaLaunchKernelEx(&cfg, emd_auction_kernel<false>, p1, p2, N, eps, iters, (int)with_x1, dist, (int *)assignment, (int *)stats, (long long *)nullptr));
+        PCL_CUDA(cudaLaunchKernelEx(&cfg, emd_auction_kernel<false>, p1, p2, N, eps, iters, flags, pcap, dist, (int *)assignment, (int *)stats, (long long *)nullptr));
     }
     return PCL_OK;
 }

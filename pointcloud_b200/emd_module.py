@@ -18,8 +18,8 @@ from . import _lib
 
 
 def emd_forward_raw(xyz1, xyz2, eps, iters, want_stats=False):
-    """One pcl_emd_fwd call.  Returns (dist, assignment, stats|None); stats int32 (B,4) =
-    [sum_t U_t, iterations run, extra GetMax qualifiers, cluster size]."""
+    """One pcl_emd_fwd call.  Returns (dist, assignment, stats|None); stats int32 (B,8) =
+    [sum_t U_t, iterations run, extra GetMax qualifiers, cluster size, executed evals lo, hi, flags, tiles]."""
     _lib.require_cuda()
     L = _lib.lib()
     xyz1, xyz2 = _lib.as_points(xyz1), _lib.as_points(xyz2)
@@ -29,7 +29,7 @@ def emd_forward_raw(xyz1, xyz2, eps, iters, want_stats=False):
     with torch.cuda.device(dev):
         dist = torch.empty(b, n, device=dev, dtype=torch.float32)
         assignment = torch.empty(b, n, device=dev, dtype=torch.int32)
-        stats = torch.empty(b, 4, device=dev, dtype=torch.int32) if want_stats else None
+        stats = torch.empty(b, 8, device=dev, dtype=torch.int32) if want_stats else None
         wsb = L.pcl_emd_workspace_bytes(b, n)
         ws = torch.empty(wsb, device=dev, dtype=torch.uint8)
         rc = L.pcl_emd_fwd(*_lib.pts_args(xyz1), *_lib.pts_args(xyz2), b, n, float(eps), int(iters),

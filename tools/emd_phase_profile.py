@@ -17,7 +17,7 @@ for kind in ("uniform", "table", "noisy"):
         x2 = t[:, :, :3].contiguous()
     x1, x2 = x1.cuda(), x2.cuda()
     dist = torch.empty(b, n, device="cuda"); asg = torch.empty(b, n, device="cuda", dtype=torch.int32)
-    stats = torch.empty(b, 4, device="cuda", dtype=torch.int32)
+    stats = torch.empty(b, 8, device="cuda", dtype=torch.int32)
     wsb = L.pcl_emd_workspace_bytes(b, n); ws = torch.zeros(wsb, device="cuda", dtype=torch.uint8)
     for _ in range(3):
         ws.zero_()
@@ -30,11 +30,7 @@ for kind in ("uniform", "table", "noisy"):
     print(f"{kind}: cs={cs} iters_run={stats[:,1].tolist()[:6]}.. per-CTA total cycles mean={tot.mean():.0f} max={tot.max():.0f}")
     for i, nm in enumerate(names):
         print(f"   {nm:13s} mean {prof[:,:,i].mean():10.0f} cyc ({100*prof[:,:,i].mean()/tot.mean():5.1f}%)  max {prof[:,:,i].max():10.0f}")
-    it = ws.view(torch.int64)[b * cs * 8: b * cs * 8 + 100].view(50, 2).cpu()
-    print("   per-iteration (U, bid cycles of CTA0):", [(int(u), int(c)) for u, c in it.tolist()][:50])
-    sub = ws.view(torch.int64)[b * cs * 8 + 128: b * cs * 8 + 128 + 200].view(50, 4).cpu()
-    print("   sub-phase ticks (after load, init, scan, sync) per iteration:", sub.tolist()[:50:3])
-    cnt = ws.view(torch.int64)[b * cs * 8 + 400: b * cs * 8 + 408].cpu().tolist()
-    for nm, c in (("iteration 0", cnt[:3]), ("iterations >= 1", cnt[4:7])):
-        ev, sg, ex = c
-        print(f"   {nm}: evals={ev} slow groups={sg} ({100*sg/max(ev/4,1):.1f}% of groups) exact evals={ex} ({100*ex/max(ev,1):.2f}% of evals)")
+    ev = (stats[:, 4].long() & 0xffffffff) + (stats[:, 5].long() << 32)
+    print(f"   executed evals / algorithmic evals = {ev.sum().item() / (stats[:,0].long().sum().item() * n):.3f}")
+    it = ws.view(torch.int64)[b * cs * 8: b * cs * 8 + 200].view(50, 4).cpu().tolist()
+    print("   per-iteration (U, bid cyc, KS*1000+Gn, wait cyc) of CTA0:", [tuple(int(v) for v in r) for r in it][:50])

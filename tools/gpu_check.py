@@ -101,7 +101,8 @@ def timings(ref):
         t_emd = timeit(lambda: pcl.emd_forward_raw(x1, x2, 0.005, 50))
         _, _, st = pcl.emd_forward_raw(x1, x2, 0.005, 50, want_stats=True)
         su = st[:, 0].sum().item()
-        msg = f"time {kind} B=32 N=2048: emd_fwd {t_emd*1e3:.1f} us  sumU={su} -> {su*n/t_emd/1e6:.1f} G pair-evals/s"
+        ev = ((st[:, 4].long() & 0xffffffff) + (st[:, 5].long() << 32)).sum().item()
+        msg = f"time {kind} B=32 N=2048: emd_fwd {t_emd*1e3:.1f} us  sumU={su} -> {su*n/t_emd/1e6:.1f} G pair-evals/s (executed {ev/(su*n):.3f})"
         if ref is not None:
             t_ref = timeit(lambda: ref_emd(ref, x1, x2, 0.005, 50), iters=5, warm=1)
             msg += f" | reference ext {t_ref*1e3:.1f} us"
