@@ -285,7 +285,7 @@ def main():
     # ---- per-kernel breakdown on rank 0's stream (explains `value`; same inputs, events around each phase) ----
     phases = {"chamfer_fwd_bwd": [], "emd_fwd": [], "emd_reduce_bwd": []}
     per_regime = {"independent": [], "noisy": []}
-    sum_u = []
+    sum_u, executed = [], []
     for i in range(min(K, 32)):
         p, t, regime = pool[(W + i) % n_sets]
         a, b_, c, d = ev(), ev(), ev(), ev()
@@ -294,6 +294,7 @@ def main():
         phases["chamfer_fwd_bwd"].append(a.elapsed_time(b_)); phases["emd_fwd"].append(b_.elapsed_time(c)); phases["emd_reduce_bwd"].append(c.elapsed_time(d))
         per_regime[regime].append(a.elapsed_time(d))
         sum_u.append(int(step.stats[:, 0].sum().item()))
+        executed.append(int(((step.stats[:, 4].long() & 0xffffffff) + (step.stats[:, 5].long() << 32)).sum().item()))
     emd_ms = statistics.mean(phases["emd_fwd"])
     evals = statistics.mean(sum_u) * NPTS  # pair evaluations one auction launch executes (sum_t U_t * N over the batch)
     sm_count = ctypes.c_int(0)
@@ -309,7 +310,10 @@ def main():
                 "peak_source": f"{sm_count.value} SMs x 128 lanes x 2 FLOP x {sm_max:.0f} MHz (MEASURED_PEAKS.json sm_max_mhz); "
                                "contraction depth 3 => CUDA-core bound, neither hbm nor tensor (SURVEY.md 8d)",
                 "algorithmic": f"{FLOP_PER_EMD_EVAL} FLOP x N x sum_t U_t = {FLOP_PER_EMD_EVAL * evals:.3e} FLOP per launch",
-                "pair_evals_per_s": evals / (emd_ms * 1e-3), "avg_launch_ms": emd_ms}
+                "pair_evals_per_s": evals / (emd_ms * 1e-3), "avg_launch_ms": emd_ms,
+                "executed_fraction": statistics.mean(executed) / evals,
+                "executed_note": "algorithmic = every (bidder, target) pair of the reference's Bid (N * sum_t U_t); the kernel proves "
+                                 "whole 32-target tiles irrelevant with an exact bounding-box test and really evaluates only this fraction"}
     ch_evals = 2.0 * B_PER_GPU * NPTS * NPTS
     breakdown = {k: statistics.mean(v) for k, v in phases.items()}
     breakdown["ms_per_step_independent"] = statistics.mean(per_regime["independent"]) if per_regime["independent"] else None
