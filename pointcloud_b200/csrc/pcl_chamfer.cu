@@ -10,6 +10,8 @@
 // broadcast LDS.128 feeds QPT distance evaluations per thread); distance arithmetic is written with
 // explicit __fmul_rn/__fadd_rn/__fmaf_rn so that the compiler cannot re-associate or contract it
 // differently from the oracle (bit-exact distances => bit-exact argmin).
+#include <stdlib.h>
+
 #include "pcl_common.cuh"
 
 namespace pcl {
@@ -17,6 +19,7 @@ namespace {
 
 constexpr int CH_THREADS = 128;
 constexpr int CH_TILE = 1024;  // targets per shared-memory tile (16 KB)
+constexpr int CH_CHUNK = 64;   // argmin recovery granularity
 
 template <bool FMA>
 __device__ __forceinline__ float sqdist3(float qx, float qy, float qz, const float4 &t) {
@@ -25,25 +28,35 @@ __device__ __forceinline__ float sqdist3(float qx, float qy, float qz, const flo
     else return __fadd_rn(__fadd_rn(__fmul_rn(dx, dx), __fmul_rn(dy, dy)), __fmul_rn(dz, dz));
 }
 
-__device__ __forceinline__ float block_sum_128(float v, float *red /* >= 4 floats */) {
+template <int NWARPS>
+__device__ __forceinline__ float block_sum(float v, float *red /* >= NWARPS floats */) {
 #pragma unroll
     for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
     const int w = threadIdx.x >> 5;
     if ((threadIdx.x & 31) == 0) red[w] = v;
     __syncthreads();
     float s = 0.f;
-    if (threadIdx.x == 0) s = (red[0] + red[1]) + (red[2] + red[3]);
+    if (threadIdx.x == 0) {
+#pragma unroll
+        for (int i = 0; i < NWARPS; i++) s += red[i];  // fixed order
+    }
     return s;  // valid on thread 0
 }
 
-// grid: (ceil(maxP / (128*QPT)), B, 2 directions)
-template <bool FMA, int QPT>
-__global__ void __launch_bounds__(CH_THREADS)
+// grid: (ceil(maxP / (128*QPT)), B, 2 directions); block: 128 query lanes x KSP target parts.
+// A CTA owns 128*QPT queries; its KSP groups of 4 warps scan interleaved 64-target chunks of every tile, so that
+// even the small (B=32, N=2048) problem keeps ~28 warps per SM busy while one broadcast LDS.128 still feeds QPT
+// evaluations.  Per evaluation only the running minimum is tracked (one FMNMX next to the 8 FMA-pipe operations);
+// the argmin is recovered per chunk, and parts are merged with an explicit lowest-index rule.
+template <bool FMA, int QPT, int KSP>
+__global__ void __launch_bounds__(CH_THREADS * KSP)
 chamfer_nn3_kernel(Pts x, const int64_t *__restrict__ x_len, Pts y, const int64_t *__restrict__ y_len, int P1, int P2,
                    float *__restrict__ dist_x, int *__restrict__ idx_x, float *__restrict__ dist_y,
                    int *__restrict__ idx_y, float *__restrict__ partial, int nblk) {
+    constexpr int NT = CH_THREADS * KSP;
     __shared__ float4 tile[CH_TILE];
-    __shared__ float red[4];
+    __shared__ float red[NT / 32];
+    static_assert(sizeof(float4) * CH_TILE >= (size_t)CH_THREADS * QPT * KSP * 8, "merge buffer aliases the tile");
     const int dir = blockIdx.z, n = blockIdx.y;
     const Pts q = dir ? y : x, t = dir ? x : y;
     const int PQ = dir ? P2 : P1;
@@ -53,50 +66,92 @@ chamfer_nn3_kernel(Pts x, const int64_t *__restrict__ x_len, Pts y, const int64_
     const int lt = dir ? (x_len ? (int)x_len[n] : P1) : (y_len ? (int)y_len[n] : P2);
     float *dist = (dir ? dist_y : dist_x) + (size_t)n * PQ;
     int *idx = (dir ? idx_y : idx_x) + (size_t)n * PQ;
+    const int ql = threadIdx.x & (CH_THREADS - 1), part = threadIdx.x / CH_THREADS;
 
     float qx[QPT], qy[QPT], qz[QPT], best[QPT];
-    int bi[QPT];
+    int bi[QPT], bchunk[QPT];
+    bool improved[QPT];
 #pragma unroll
     for (int r = 0; r < QPT; r++) {
-        const int i = q0 + r * CH_THREADS + threadIdx.x;
+        const int i = q0 + r * CH_THREADS + ql;
         float3 p = make_float3(0.f, 0.f, 0.f);
         if (i < lq) p = ld_xyz(q, n, i);
         qx[r] = p.x; qy[r] = p.y; qz[r] = p.z;
         best[r] = __int_as_float(0x7f800000);  // +inf
-        bi[r] = 0;
+        bi[r] = 0x7fffffff; bchunk[r] = 0; improved[r] = false;
     }
     if (q0 < lq) {  // block-uniform: blocks made only of padded rows skip the scan
         for (int t0 = 0; t0 < lt; t0 += CH_TILE) {
             const int cnt = min(CH_TILE, lt - t0);
-            for (int j = threadIdx.x; j < cnt; j += CH_THREADS) {
+            for (int j = threadIdx.x; j < cnt; j += NT) {
                 const float3 p = ld_xyz(t, n, t0 + j);
                 tile[j] = make_float4(p.x, p.y, p.z, 0.f);
             }
             __syncthreads();
-#pragma unroll 4
-            for (int j = 0; j < cnt; j++) {
-                const float4 tp = tile[j];
+            // strict '<' between this part's chunks (ascending) keeps its earliest chunk; the re-scan below returns the
+            // lowest index inside it -- together with the index-aware merge: "lowest index wins ties", as in knn's scan.
+            for (int c0 = part * CH_CHUNK; c0 < cnt; c0 += CH_CHUNK * KSP) {
+                const int c1 = min(c0 + CH_CHUNK, cnt);
+                float mc[QPT];
 #pragma unroll
-                for (int r = 0; r < QPT; r++) {
-                    const float d = sqdist3<FMA>(qx[r], qy[r], qz[r], tp);
-                    if (d < best[r]) { best[r] = d; bi[r] = t0 + j; }  // strict '<': lowest index wins ties
+                for (int r = 0; r < QPT; r++) mc[r] = __int_as_float(0x7f800000);
+#pragma unroll 8
+                for (int j = c0; j < c1; j++) {
+                    const float4 tp = tile[j];
+#pragma unroll
+                    for (int r = 0; r < QPT; r++) mc[r] = fminf(mc[r], sqdist3<FMA>(qx[r], qy[r], qz[r], tp));
+                }
+#pragma unroll
+                for (int r = 0; r < QPT; r++)
+                    if (mc[r] < best[r]) { best[r] = mc[r]; bchunk[r] = c0; improved[r] = true; }
+            }
+#pragma unroll
+            for (int r = 0; r < QPT; r++) {
+                if (improved[r]) {  // the tile is still in shared memory: find the first index that attains the minimum
+                    const int c0 = bchunk[r], c1 = min(c0 + CH_CHUNK, cnt);
+                    for (int j = c1 - 1; j >= c0; j--)
+                        if (sqdist3<FMA>(qx[r], qy[r], qz[r], tile[j]) == best[r]) bi[r] = t0 + j;
+                    improved[r] = false;
                 }
             }
             __syncthreads();
         }
     }
-    float s = 0.f;
+    if constexpr (KSP > 1) {  // merge the parts: minimum distance, lowest index among equal minima
+        float *mb = reinterpret_cast<float *>(tile);
+        int *mi = reinterpret_cast<int *>(tile) + CH_THREADS * QPT * KSP;
 #pragma unroll
-    for (int r = 0; r < QPT; r++) {
-        const int i = q0 + r * CH_THREADS + threadIdx.x;
-        if (i < PQ) {
-            const bool valid = (i < lq) && (lt > 0);
-            const float d = valid ? best[r] : 0.f;
-            dist[i] = d; idx[i] = valid ? bi[r] : 0;
-            s += d;
+        for (int r = 0; r < QPT; r++) {
+            mb[(part * QPT + r) * CH_THREADS + ql] = best[r];
+            mi[(part * QPT + r) * CH_THREADS + ql] = bi[r];
+        }
+        __syncthreads();
+        if (part == 0) {
+#pragma unroll
+            for (int r = 0; r < QPT; r++) {
+#pragma unroll
+                for (int pp = 1; pp < KSP; pp++) {
+                    const float ob = mb[(pp * QPT + r) * CH_THREADS + ql];
+                    const int oi = mi[(pp * QPT + r) * CH_THREADS + ql];
+                    if (ob < best[r] || (ob == best[r] && oi < bi[r])) { best[r] = ob; bi[r] = oi; }
+                }
+            }
         }
     }
-    s = block_sum_128(s, red);
+    float s = 0.f;
+    if (part == 0) {
+#pragma unroll
+        for (int r = 0; r < QPT; r++) {
+            const int i = q0 + r * CH_THREADS + ql;
+            if (i < PQ) {
+                const bool valid = (i < lq) && (lt > 0);
+                const float d = valid ? best[r] : 0.f;
+                dist[i] = d; idx[i] = (valid && bi[r] != 0x7fffffff) ? bi[r] : 0;
+                s += d;
+            }
+        }
+    }
+    s = block_sum<NT / 32>(s, red);
     if (threadIdx.x == 0) partial[((size_t)dir * gridDim.y + n) * nblk + blockIdx.x] = s;
 }
 
@@ -152,7 +207,7 @@ chamfer_nnD_kernel(Pts x, const int64_t *__restrict__ x_len, Pts y, const int64_
         s = valid ? best : 0.f;
         dist[i] = s; idx[i] = valid ? bi : 0;
     }
-    s = block_sum_128(s, red);
+    s = block_sum<4>(s, red);
     if (threadIdx.x == 0) partial[((size_t)dir * gridDim.y + n) * nblk + blockIdx.x] = s;
 }
 
@@ -211,16 +266,25 @@ int launch_fwd(const Pts &x, const int64_t *x_len, const Pts &y, const int64_t *
                cudaStream_t st) {
     const int maxP = P1 > P2 ? P1 : P2;
     if (D == 3) {
-        // pick queries-per-thread so that the grid still covers the chip several times over
+        // 128*QPT queries per CTA; KSP target parts per CTA keep the warp count per SM high on small problems
         const long queries = (long)B * ((long)P1 + P2);
         int qpt = 4;
         while (qpt > 1 && queries / (CH_THREADS * qpt) < 6L * sm_count) qpt >>= 1;
+        int ksp = 1;  // target-part split: measured slower on B200 at every size tried (profiles/r1_chamfer_variants.txt); kept as an option
+        if (const char *e = getenv("PCL_CHAMFER_QPT")) { const int v = atoi(e); if (v == 1 || v == 2 || v == 4) qpt = v; }  // development aid
+        if (const char *e = getenv("PCL_CHAMFER_KSP")) { const int v = atoi(e); if (v == 1 || v == 4) ksp = v; }
         dim3 grid((maxP + CH_THREADS * qpt - 1) / (CH_THREADS * qpt), B, 2);
-#define PCL_LAUNCH_NN3(Q) \
-    chamfer_nn3_kernel<FMA, Q><<<grid, CH_THREADS, 0, st>>>(x, x_len, y, y_len, P1, P2, dist_x, idx_x, dist_y, idx_y, partial, nblk)
-        if (qpt == 4) PCL_LAUNCH_NN3(4);
-        else if (qpt == 2) PCL_LAUNCH_NN3(2);
-        else PCL_LAUNCH_NN3(1);
+#define PCL_LAUNCH_NN3(Q, K) \
+    chamfer_nn3_kernel<FMA, Q, K><<<grid, CH_THREADS * K, 0, st>>>(x, x_len, y, y_len, P1, P2, dist_x, idx_x, dist_y, idx_y, partial, nblk)
+        if (ksp == 4) {
+            if (qpt == 4) PCL_LAUNCH_NN3(4, 4);
+            else if (qpt == 2) PCL_LAUNCH_NN3(2, 4);
+            else PCL_LAUNCH_NN3(1, 4);
+        } else {
+            if (qpt == 4) PCL_LAUNCH_NN3(4, 1);
+            else if (qpt == 2) PCL_LAUNCH_NN3(2, 1);
+            else PCL_LAUNCH_NN3(1, 1);
+        }
 #undef PCL_LAUNCH_NN3
     } else {
         dim3 grid((maxP + CH_THREADS - 1) / CH_THREADS, B, 2);
