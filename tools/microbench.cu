@@ -8,7 +8,7 @@
 constexpr int ITER = 4096;
 constexpr int U = 8;
 
-enum Op { FFMA, FADD, FMNMX, IADD, DADD, F2D, D2F, RSQ, SQRT_RN, BID_REF, BID_MANUAL, BID_F32ONLY, LDS_B128 };
+enum Op { FFMA, FADD, FMNMX, IADD, DADD, F2D, D2F, RSQ, SQRT_RN, BID_REF, BID_MANUAL, BID_F32ONLY, LDS_B128, FMUL, DIST_UNFUSED, DIST_FMA, DIST_UNFUSED_LDS };
 
 __device__ __forceinline__ float manual_d2f(double t) {  // RNE double->float for normal-range positive results
     const unsigned lo = (unsigned)__double2loint(t), hi = (unsigned)__double2hiint(t);
@@ -37,6 +37,17 @@ __global__ void __launch_bounds__(256) probe(float *out, float seed, double dsee
         for (int u = 0; u < U; u++) {
             if (OP == FFMA) f[u] = __fmaf_rn(f[u], 1.0001f, 0.5f);
             else if (OP == FADD) f[u] = __fadd_rn(f[u], seed);
+            else if (OP == FMUL) f[u] = __fmul_rn(f[u], 1.0000001f);
+            else if (OP == DIST_UNFUSED || OP == DIST_FMA || OP == DIST_UNFUSED_LDS) {
+                float4 t = make_float4(seed + i, seed * 2, seed * 3 + u, 0.f);
+                if (OP == DIST_UNFUSED_LDS) t = tile[(i + (u >> 2)) & 255];
+                const float qx = (float)n[u], qy = (float)d[u], qz = seed * u;
+                const float dx = __fsub_rn(qx, t.x), dy = __fsub_rn(qy, t.y), dz = __fsub_rn(qz, t.z);
+                float dd;
+                if (OP == DIST_FMA) dd = __fmaf_rn(dz, dz, __fmaf_rn(dy, dy, __fmul_rn(dx, dx)));
+                else dd = __fadd_rn(__fadd_rn(__fmul_rn(dx, dx), __fmul_rn(dy, dy)), __fmul_rn(dz, dz));
+                f[u] = fminf(f[u], dd);
+            }
             else if (OP == FMNMX) f[u] = fmaxf(f[u], seed + (float)i);
             else if (OP == IADD) n[u] = (n[u] ^ i) + u;
             else if (OP == DADD) d[u] = __dadd_rn(d[u], dseed);
@@ -115,6 +126,10 @@ int main() {
     run<RSQ>("MUFU.RSQ+1", out, sms, r0);
     run<SQRT_RN>("sqrt.rn+1", out, sms, r0);
     run<LDS_B128>("LDS.128+1", out, sms, r0);
+    run<FMUL>("FMUL", out, sms, r0);
+    run<DIST_UNFUSED>("dist_unfused(9)", out, sms, r0);
+    run<DIST_FMA>("dist_fma(7)", out, sms, r0);
+    run<DIST_UNFUSED_LDS>("dist_unf+LDS/4", out, sms, r0);
     run<BID_REF>("bid_ref", out, sms, r0);
     run<BID_MANUAL>("bid_manual", out, sms, r0);
     run<BID_F32ONLY>("bid_f32only", out, sms, r0);
