@@ -56,7 +56,7 @@ class ClockSampler:
 
     def start(self):
         try:
-            self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-lms", "100",
+            self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-lms", "20",
                                           "-i", str(self.gpu)], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
             self.t = threading.Thread(target=self._read, daemon=True)
             self.t.start()
@@ -84,8 +84,9 @@ class ClockSampler:
             for name, val in zip(["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"], f[5:9]):
                 if val.lower().startswith("active"):
                     reasons.add(name)
-        if not sm:  # region shorter than one sample: take the nearest samples
-            for ts, line in self.lines[-3:]:
+        if not sm:  # region shorter than one sample period: take the samples nearest to it
+            near = sorted(self.lines, key=lambda tl: min(abs(tl[0] - t0), abs(tl[0] - t1)))[:3]
+            for ts, line in near:
                 f = [x.strip() for x in line.split(",")]
                 try:
                     sm.append(float(f[1])); mx.append(float(f[2]))
@@ -217,7 +218,7 @@ def run_reference(args):
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=60)
+    ap.add_argument("--steps", type=int, default=300)
     ap.add_argument("--warmup", type=int, default=5)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
@@ -257,6 +258,8 @@ def main():
         return x
 
     K, W = args.steps, args.warmup
+    sampler = ClockSampler(local)
+    sampler.start()  # started early: nvidia-smi needs a few hundred ms before its first sample
     n_sets = 96  # 96 * 1.57 MB of inputs = 151 MB > 126 MB L2: every step reads inputs that are not L2-resident
     pool = make_pool(torch, synth, device, rank, n_sets)
     step = DeviceStep(torch, _lib, device)
@@ -266,8 +269,6 @@ def main():
     # ---- value: device-resident inputs, whole step, CUDA events on the launching stream ---------------
     for i in range(W):
         step(*pool[i % n_sets][:2], st)
-    sampler = ClockSampler(local)
-    sampler.start()
     barrier()
     t_wall0 = time.time()
     e0, e1 = ev(), ev()

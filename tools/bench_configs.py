@@ -1,0 +1,136 @@
+"""Secondary measurements for the BASELINE.md plan (configs 1, 3, 5; config 2 is bench.py's headline).
+
+  config 1: Chamfer fwd+bwd on the CPU, B=8, N=M=2048 (torch brute force = "reference torch path", and the oracle C port)
+  config 3: weighted EMD (Segmenter loss) fwd+bwd, B=32, N=2048, C=5, through the Python loss class
+  config 5: Chamfer fwd+bwd, B=64, N=M in {1024..16384}, one GPU (C ABI, preallocated outputs)
+Writes one JSON object to stdout.  Run on the GPU box: python tools/bench_configs.py > gpurun_out/configs.json
+"""
+import json
+import os
+import sys
+import time
+
+import torch
+
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+import oracle  # noqa: E402  (CPU baseline leg only)
+import pointcloud_b200 as pcl  # noqa: E402
+from pointcloud_b200 import _lib, synth  # noqa: E402
+
+
+def ev_time(fn, iters, warm=3):
+    for _ in range(warm):
+        fn()
+    torch.cuda.synchronize()
+    a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    a.record()
+    for _ in range(iters):
+        fn()
+    b.record()
+    torch.cuda.synchronize()
+    return a.elapsed_time(b) / iters
+
+
+def config1():
+    b, n = 8, 2048
+    pred, target = synth.table_clouds(b, n, seed=0)
+    x, y = pred, target[:, :, :3].contiguous()
+    out = {"shape": [b, n, n], "cpu_count": os.cpu_count()}
+
+    def torch_path():
+        xx, yy = x.clone().requires_grad_(), y.clone().requires_grad_()
+        d = ((xx[:, :, None, :] - yy[:, None, :, :]) ** 2).sum(-1)
+        loss = d.min(2).values.mean(1).mean() + d.min(1).values.mean(1).mean()
+        loss.backward()
+
+    for th in (os.cpu_count(), 1):
+        torch.set_num_threads(th)
+        torch_path()
+        t0 = time.perf_counter()
+        reps = 3 if th > 1 else 1
+        for _ in range(reps):
+            torch_path()
+        dt = (time.perf_counter() - t0) / reps
+        out[f"torch_cpu_{th}_threads_ms"] = dt * 1e3
+        out[f"torch_cpu_{th}_threads_clouds_per_s"] = b / dt
+    torch.set_num_threads(os.cpu_count())
+
+    def port(th):
+        c = oracle.chamfer_forward(x, y, nthreads=th)
+        oracle.chamfer_backward(x, y, c["idx_x"], c["idx_y"], 1.0)
+
+    for th in (min(os.cpu_count(), b), 1):
+        port(th)
+        t0 = time.perf_counter()
+        for _ in range(3):
+            port(th)
+        dt = (time.perf_counter() - t0) / 3
+        out[f"oracle_port_{th}_threads_ms"] = dt * 1e3
+    # the same batch on the GPU through the public API
+    xg, yg = x.cuda(), y.cuda()
+
+    def gpu():
+        xx = xg.clone().requires_grad_()
+        l, _ = pcl.chamfer_distance(xx, yg)
+        l.backward()
+
+    out["gpu_api_ms"] = ev_time(gpu, 50)
+    return out
+
+
+def config3():
+    b, n, c = 32, 2048, 5
+    out = {"shape": [b, n, 3 + c]}
+    for regime in ("independent", "noisy"):
+        pred, target = synth.segmenter_batch(b, n, seed=0, regime=regime)
+        pg, tg = pred.cuda(), target.cuda()
+        for fused in (True, False):
+            fn = pcl.EarthMoverDistance(eps=0.005, its=50, num_classes=c, fused=fused)
+
+            def step():
+                p = pg.clone().requires_grad_()
+                loss = fn(p, tg)
+                loss.backward()
+
+            ms = ev_time(step, 20)
+            out[f"{regime}_{'fused' if fused else 'reference_structure'}_ms"] = ms
+            out[f"{regime}_{'fused' if fused else 'reference_structure'}_clouds_per_s"] = b / (ms * 1e-3)
+    return out
+
+
+def config5():
+    L = _lib.lib()
+    A = _lib.pts_args
+    b = 64
+    rows = []
+    for n in (1024, 2048, 4096, 8192, 16384):
+        x, y = synth.uniform_clouds(b, n, seed=0)
+        x, y = x.cuda(), y.cuda()
+        e = lambda *s, dt=torch.float32: torch.empty(*s, device="cuda", dtype=dt)
+        dx, dy, ix, iy, lxy = e(b, n), e(b, n), e(b, n, dt=torch.int32), e(b, n, dt=torch.int32), e(2)
+        gx, gy, ones = e(b, n, 3), e(b, n, 3), torch.ones(2, device="cuda")
+        wsb = L.pcl_chamfer_workspace_bytes(b, n, n)
+        ws = torch.empty(wsb, device="cuda", dtype=torch.uint8)
+
+        def fwd():
+            assert L.pcl_chamfer_fwd(*A(x), None, *A(y), None, b, n, n, 3, 0, dx.data_ptr(), ix.data_ptr(), dy.data_ptr(), iy.data_ptr(),
+                                     lxy.data_ptr(), ws.data_ptr(), wsb, None) == 0
+
+        def bwd():
+            assert L.pcl_chamfer_bwd(*A(x), None, *A(y), None, b, n, n, 3, ix.data_ptr(), iy.data_ptr(), ones.data_ptr(), gx.data_ptr(),
+                                     gy.data_ptr(), None) == 0
+
+        it = 50 if n <= 4096 else 10
+        tf, tb = ev_time(fwd, it), ev_time(bwd, it)
+        evals = 2.0 * b * n * n
+        rows.append({"N": n, "fwd_ms": tf, "bwd_ms": tb, "clouds_per_s": b / ((tf + tb) * 1e-3),
+                     "directed_pair_evals_per_s": evals / (tf * 1e-3), "fp32_flop_frac_of_74.4T": 8 * evals / (tf * 1e-3) / 74.45e12,
+                     "bwd_GBps_algorithmic": 2 * b * n * 56 / (tb * 1e-3) / 1e9})
+    return {"B": b, "rows": rows}
+
+
+if __name__ == "__main__":
+    res = {"gpu": torch.cuda.get_device_name(0), "config1_chamfer_cpu_B8_N2048": config1(), "config3_weighted_emd_B32_N2048_C5": config3(),
+           "config5_chamfer_sweep_B64": config5(),
+           "config4": "not measured: needs the PointNet2 model zoo (SURVEY.md 2, out of scope) as the producer of pred"}
+    print(json.dumps(res, indent=1))

@@ -35,7 +35,7 @@ def stalls(rep):
     tot = defaultdict(int)
     samples = 0
     for r in rows[2:]:
-        if len(r) < len(hdr):
+        if len(r) < len(hdr) or r[ci["# Samples"]] == "# Samples":  # short rows / repeated headers of further launches
             continue
         samples += int(r[ci["# Samples"]] or 0)
         for s in names:
