@@ -38,7 +38,8 @@ namespace {
 
 constexpr int EMD_THREADS = 512;
 constexpr int EMD_WARPS = EMD_THREADS / 32;
-constexpr int EMD_MAX_N = 4096;
+constexpr int EMD_MAX_N = 8192;      // 4097..8192: the cold half of the state lives in a per-CTA global-memory region (L2)
+constexpr int EMD_SMEM_ONLY_N = 4096;  // up to here the whole auction state fits into shared memory
 constexpr int TILE = 32;  // targets per spatial tile (one bounding box per tile)
 constexpr int EMD_WPB_MAX = 4 * EMD_WARPS;  // at most this many bidders per CTA: warp-per-bidder scan
 constexpr unsigned short NONE16 = 0xffffu;
@@ -48,6 +49,7 @@ constexpr float FILTER_MARGIN = 2e-6f;  // > 4.2e-7 worst-case rounding slack of
 // flags of the launch (what fits into shared memory for this N)
 constexpr int EMD_F_SORT = 1;  // clouds are re-ordered along a Morton curve inside the kernel
 constexpr int EMD_F_X1 = 2;    // predictions are cached in shared memory
+constexpr int EMD_F_COLD = 4;  // bids / per-object maxima / assignment arrays live in global memory (large N)
 
 struct EmdSmem {
     float4 *tgt;            // n32 {x, y, z, c = RU(3 - price)}, internal (sorted) target order, padded with far sentinels
@@ -69,35 +71,41 @@ struct EmdSmem {
     float4 *x1;             // N   predictions {x,y,z,0} in internal order (nullptr: read from global/L2)
 };
 
+// bytes of the "cold" arrays (touched O(U) times per iteration): pub 16, maxinc 4, maxidx 4, last 4, asg/inv/unass 6
+__host__ __device__ inline size_t emd_cold_bytes(int N) {
+    const size_t n8 = (size_t)(N + 7) / 8 * 8;
+    return n8 * (16 + 4 + 4 + 4) + n8 * 2 * 3;
+}
 __host__ __device__ inline size_t emd_smem_bytes(int N, int flags, int pcap = EMD_THREADS) {
     const size_t n8 = (size_t)(N + 7) / 8 * 8, n32 = (size_t)(N + 31) / 32 * 32, nt = n32 / 32;
-    return n32 * 16 + n8 * (16 + 4 + 4 + 4 + 4) + n8 * 2 * 3 + (size_t)pcap * 12 + 32 * 4 + 16 + nt * 32 +
+    return n32 * 16 + n8 * 4 + ((flags & EMD_F_COLD) ? 0 : emd_cold_bytes(N)) + (size_t)pcap * 12 + 32 * 4 + 16 + nt * 32 +
            ((flags & EMD_F_SORT) ? n8 * 4 : 0) + ((flags & EMD_F_X1) ? n8 * 16 : 0) + 64;
 }
 
-__device__ inline EmdSmem carve(unsigned char *base, int N, int flags, int pcap) {
+__device__ inline EmdSmem carve(unsigned char *base, unsigned char *cold, int N, int flags, int pcap) {
     const size_t n8 = (size_t)(N + 7) / 8 * 8, n32 = (size_t)(N + 31) / 32 * 32, nt = n32 / 32;
     EmdSmem s;
     unsigned char *p = base;
     s.tgt = (float4 *)p; p += n32 * 16;
-    s.pub = (uint2 *)p; p += n8 * 16;
     s.tlo = (float4 *)p; p += nt * 16;
     s.thi = (float4 *)p; p += nt * 16;
     s.x1 = (flags & EMD_F_X1) ? (float4 *)p : nullptr; p += (flags & EMD_F_X1) ? n8 * 16 : 0;
-    s.asg = (unsigned short *)p; p += n8 * 2;   // 16-byte aligned for the uint4 reads of the compaction
-    s.inv = (unsigned short *)p; p += n8 * 2;
-    s.unass = (unsigned short *)p; p += n8 * 2;
     s.tperm = (flags & EMD_F_SORT) ? (unsigned short *)p : nullptr; p += (flags & EMD_F_SORT) ? n8 * 2 : 0;
     s.pperm = (flags & EMD_F_SORT) ? (unsigned short *)p : nullptr; p += (flags & EMD_F_SORT) ? n8 * 2 : 0;
     s.pf = (float *)p; p += n8 * 4;
-    s.maxinc = (float *)p; p += n8 * 4;
-    s.maxidx = (int *)p; p += n8 * 4;
-    s.last = (unsigned *)p; p += n8 * 4;
     s.pbest = (float *)p; p += (size_t)pcap * 4;
     s.pbetter = (float *)p; p += (size_t)pcap * 4;
     s.pbi = (unsigned *)p; p += (size_t)pcap * 4;
     s.wsum = (int *)p; p += 32 * 4;
     s.evals = (unsigned long long *)p; p += 16;
+    unsigned char *c = (flags & EMD_F_COLD) ? cold : p;  // same layout in shared memory or in the CTA's global region
+    s.pub = (uint2 *)c; c += n8 * 16;
+    s.asg = (unsigned short *)c; c += n8 * 2;   // 16-byte aligned for the uint4 reads of the compaction
+    s.inv = (unsigned short *)c; c += n8 * 2;
+    s.unass = (unsigned short *)c; c += n8 * 2;
+    s.maxinc = (float *)c; c += n8 * 4;
+    s.maxidx = (int *)c; c += n8 * 4;
+    s.last = (unsigned *)c; c += n8 * 4;
     return s;
 }
 
@@ -218,7 +226,8 @@ __device__ __forceinline__ Top2 top2_init(const EmdSmem &S, unsigned lastpack, i
 template <bool PROF>
 __global__ void __launch_bounds__(EMD_THREADS, 1)
 emd_auction_kernel(Pts xyz1, Pts xyz2, int N, float eps, int iters, int flags, int pcap, float *__restrict__ dist,
-                   int *__restrict__ assignment, int *__restrict__ stats, long long *__restrict__ prof) {
+                   int *__restrict__ assignment, int *__restrict__ stats, long long *__restrict__ prof,
+                   unsigned char *__restrict__ cold_ws) {
     long long pt[8] = {0, 0, 0, 0, 0, 0, 0, 0}, pc = 0;
 #define PCL_TICK(i)                                              \
     if constexpr (PROF) {                                        \
@@ -232,7 +241,8 @@ emd_auction_kernel(Pts xyz1, Pts xyz2, int N, float eps, int iters, int flags, i
     const int cs = (int)cluster.num_blocks(), rank = (int)cluster.block_rank();
     const int cloud = blockIdx.x / cs;
     const int tid = threadIdx.x, T = EMD_THREADS, lane = tid & 31, wid = tid >> 5;
-    const EmdSmem S = carve(smem_raw, N, flags, pcap);
+    const size_t cold_stride = (emd_cold_bytes(N) + 255) / 256 * 256;
+    const EmdSmem S = carve(smem_raw, (flags & EMD_F_COLD) ? cold_ws + (size_t)blockIdx.x * cold_stride : nullptr, N, flags, pcap);
     int *const work_ctr = S.wsum + 24;  // dynamic work-item counter of the bid phase (wsum[0..15] = warp sums)
     const int n8 = (N + 7) / 8 * 8, n32 = (N + 31) / 32 * 32, NT = n32 / TILE;
 
@@ -380,7 +390,13 @@ emd_auction_kernel(Pts xyz1, Pts xyz2, int N, float eps, int iters, int flags, i
         auto publish = [&](int jp, float best, float better, unsigned pack) {
             const float inc = __fadd_rn(__fsub_rn(best, better), eps);  // emd_cuda.cu:175
             const uint2 v = make_uint2(pack, __float_as_uint(inc));
-            for (int c = 0; c < cs; c++) cluster.map_shared_rank(pub_cur, c)[jp] = v;
+            if (flags & EMD_F_COLD) {  // peers' bid buffers are global-memory regions: plain stores, ordered by the cluster barrier
+                const size_t off = (size_t)(pub_cur - S.pub) + (size_t)jp;
+                for (int c = 0; c < cs; c++)
+                    reinterpret_cast<uint2 *>(cold_ws + ((size_t)cloud * cs + c) * cold_stride)[off] = v;
+            } else {
+                for (int c = 0; c < cs; c++) cluster.map_shared_rank(pub_cur, c)[jp] = v;
+            }
         };
 
         if (wpb) {
@@ -762,12 +778,19 @@ extern "C" int pcl_emd_max_points(void) { return EMD_MAX_N; }
 extern "C" size_t pcl_emd_workspace_bytes(int B, int N) {
     (void)N;
     const size_t red = (size_t)RED_BLOCKS * 2 * sizeof(double), prof = ((size_t)(B > 0 ? B : 0) * 16 * 8 + 512) * sizeof(long long);
-    return align_up(red > prof ? red : prof, 256);
+    size_t cold = 0;
+    if (N > EMD_SMEM_ONLY_N && B > 0) {  // large clouds: per-CTA global region for the cold state, sized for the largest cluster
+        int cs = 16;
+        while (cs > 1 && (long)B * cs > 148) cs >>= 1;
+        cold = (size_t)B * cs * ((emd_cold_bytes(N) + 255) / 256 * 256);
+    }
+    const size_t m = red > prof ? red : prof;
+    return align_up(m > cold ? m : cold, 256);
 }
 
 static int emd_check(const void *xyz1, int dtype1, const void *xyz2, int dtype2, int B, int N, const char *who) {
     if (B < 0 || N < 1) { set_error("%s: bad size B=%d N=%d", who, B, N); return PCL_E_SHAPE; }
-    if (N > EMD_MAX_N) { set_error("%s: N=%d > %d points per cloud is not supported by the shared-memory auction", who, N, EMD_MAX_N); return PCL_E_UNSUPPORTED; }
+    if (N > EMD_MAX_N) { set_error("%s: N=%d > %d points per cloud is not supported", who, N, EMD_MAX_N); return PCL_E_UNSUPPORTED; }
     if (!dtype_ok(dtype1) || !dtype_ok(dtype2)) { set_error("%s: bad dtype", who); return PCL_E_ARG; }
     if (B > 0 && (!xyz1 || !xyz2)) { set_error("%s: null input", who); return PCL_E_ARG; }
     return PCL_OK;
@@ -785,8 +808,15 @@ extern "C" int pcl_emd_fwd(const void *xyz1, int dtype1, int64_t bs1, int64_t rs
     DeviceInfo di;
     if ((rc = device_info(&di))) return rc;
     int flags = 0;
-    if (emd_smem_bytes(N, EMD_F_SORT) <= (size_t)di.max_smem_optin) flags |= EMD_F_SORT;
-    if (emd_smem_bytes(N, flags | EMD_F_X1) <= (size_t)di.max_smem_optin) flags |= EMD_F_X1;
+    if (N > EMD_SMEM_ONLY_N) {
+        flags |= EMD_F_COLD;
+        if (!workspace || workspace_bytes < pcl_emd_workspace_bytes(B, N)) {
+            set_error("emd_fwd: N=%d needs a workspace of %zu bytes (pcl_emd_workspace_bytes)", N, pcl_emd_workspace_bytes(B, N));
+            return PCL_E_WORKSPACE;
+        }
+    }
+    if (N <= EMD_SMEM_ONLY_N && emd_smem_bytes(N, EMD_F_SORT) <= (size_t)di.max_smem_optin) flags |= EMD_F_SORT;
+    if (N <= EMD_SMEM_ONLY_N && emd_smem_bytes(N, flags | EMD_F_X1) <= (size_t)di.max_smem_optin) flags |= EMD_F_X1;
     if (getenv("PCL_EMD_NO_SORT")) flags &= ~EMD_F_SORT;  // development aid: natural order (no spatial pruning benefit)
     int pcap = 4 * EMD_THREADS;  // room for 64 work items with partials; fall back to 16 when shared memory is tight
     if (emd_smem_bytes(N, flags, pcap) > (size_t)di.max_smem_optin) pcap = EMD_THREADS;
@@ -812,10 +842,10 @@ extern "C" int pcl_emd_fwd(const void *xyz1, int dtype1, int64_t bs1, int64_t rs
     const Pts p1{xyz1, bs1, rs1, dtype1}, p2{xyz2, bs2, rs2, dtype2};
     // development aid: PCL_EMD_PROFILE=1 makes the workspace receive per-phase clock totals (B*cs*8 int64)
     static const bool profile = getenv("PCL_EMD_PROFILE") != nullptr;
-    if (profile && workspace && workspace_bytes >= ((size_t)B * cs * 8 + 512) * sizeof(long long)) {
-        PCL_CUDA(cudaLaunchKernelEx(&cfg, emd_auction_kernel<true>, p1, p2, N, eps, iters, flags, pcap, dist, (int *)assignment, (int *)stats, (long long *)workspace));
+    if (profile && !(flags & EMD_F_COLD) && workspace && workspace_bytes >= ((size_t)B * cs * 8 + 512) * sizeof(long long)) {
+        PCL_CUDA(cudaLaunchKernelEx(&cfg, emd_auction_kernel<true>, p1, p2, N, eps, iters, flags, pcap, dist, (int *)assignment, (int *)stats, (long long *)workspace, (unsigned char *)nullptr));
     } else {
-        PCL_CUDA(cudaLaunchKernelEx(&cfg, emd_auction_kernel<false>, p1, p2, N, eps, iters, flags, pcap, dist, (int *)assignment, (int *)stats, (long long *)nullptr));
+        PCL_CUDA(cudaLaunchKernelEx(&cfg, emd_auction_kernel<false>, p1, p2, N, eps, iters, flags, pcap, dist, (int *)assignment, (int *)stats, (long long *)nullptr, (unsigned char *)((flags & EMD_F_COLD) ? workspace : nullptr)));
     }
     return PCL_OK;
 }

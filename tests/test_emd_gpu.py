@@ -29,6 +29,7 @@ def clouds(kind, b, n, seed):
     ("noisy", 3, 2048, 0.005, 50), ("uniform", 1, 4096, 0.005, 50), ("uniform", 5, 1000, 0.005, 50),
     ("uniform", 2, 333, 0.002, 400), ("uniform", 40, 1024, 0.005, 20), ("uniform", 1, 1, 0.005, 3),
     ("uniform", 2, 37, 0.005, 1), ("table", 2, 1024, 0.002, 3000),
+    ("uniform", 2, 8192, 0.005, 50), ("uniform", 3, 5000, 0.005, 30), ("table", 1, 6144, 0.005, 50),  # > 4096: cold state in L2
 ])
 def test_emd_forward_bit_exact_vs_oracle(kind, b, n, eps, iters):
     x1, x2 = clouds(kind, b, n, seed=100 + n)

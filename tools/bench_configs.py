@@ -129,8 +129,32 @@ def config5():
     return {"B": b, "rows": rows}
 
 
+def demo_workload():
+    """The reference's only own workload: test_emd() (emd_module.py:81-88): B=20, N=8192, eps=0.002, up to 10000 iterations."""
+    b, n, eps, iters = 20, 8192, 0.002, 10000
+    g = torch.Generator().manual_seed(0)
+    x1, x2 = torch.rand(b, n, 3, generator=g).cuda(), torch.rand(b, n, 3, generator=g).cuda()
+    out = {"shape": [b, n, 3], "eps": eps, "iters": iters}
+    t = ev_time(lambda: pcl.emd_forward_raw(x1, x2, eps, iters), 3, warm=1)
+    d, a, st = pcl.emd_forward_raw(x1, x2, eps, iters, want_stats=True)
+    out.update(ours_ms=t, iterations_run=st[:, 1].tolist(), emd=float(d.sqrt().mean()), unique=[int(r.unique().numel()) for r in a])
+    try:
+        from oracle import build_ref
+        sys.path.insert(0, os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "tests"))
+        from helpers import ref_emd_forward
+        ref = build_ref.load_ref()
+        if ref is not None:
+            tr = ev_time(lambda: ref_emd_forward(ref, x1, x2, eps, iters), 1, warm=0)
+            rd, ra = ref_emd_forward(ref, x1, x2, eps, iters)
+            out.update(reference_ext_ms=tr, reference_emd=float(rd.sqrt().mean()), reference_unique=[int(r.unique().numel()) for r in ra],
+                       identical_assignment=[bool(torch.equal(ra[i], a[i])) for i in range(b)])
+    except Exception as ex:
+        out["reference_ext"] = repr(ex)
+    return out
+
+
 if __name__ == "__main__":
     res = {"gpu": torch.cuda.get_device_name(0), "config1_chamfer_cpu_B8_N2048": config1(), "config3_weighted_emd_B32_N2048_C5": config3(),
-           "config5_chamfer_sweep_B64": config5(),
+           "config5_chamfer_sweep_B64": config5(), "reference_demo_B20_N8192": demo_workload(),
            "config4": "not measured: needs the PointNet2 model zoo (SURVEY.md 2, out of scope) as the producer of pred"}
     print(json.dumps(res, indent=1))
