@@ -148,6 +148,26 @@ PCL_API int pcl_emd_weighted_bwd(const void *xyz1, int dtype1, int64_t bs1, int6
                          const int32_t *matched_label, const float *class_weights, int C,
                          const float *sums, const float *grad_out, float *grad_xyz1, void *stream);
 
+/* ------------------------------------------------------------------ sampling ------ */
+/*
+ * Farthest point sampling: replaces pointnet2_ops._ext.furthest_point_sampling (models/pointnet2_utils.py:6,89-90)
+ * and pytorch3d.ops.sample_farthest_points (utils.py:10,90; models/pointmlp.py:158) -- third-party code that is not
+ * part of the reference tree; semantics = the torch algorithm kept as a comment in pointnet2_utils.py:64-86 with
+ * start index 0 (or start_idx[b]) and the lowest index on ties.  idx_out: int32 (B, npoint).
+ * skip_origin != 0: points with x*x+y*y+z*z <= 1e-3 are never selected (pointnet2_ops' padding convention).
+ */
+PCL_API int pcl_fps_max_points(void);
+PCL_API int pcl_fps(const void *xyz, int dtype, int64_t bs, int64_t rs, int B, int N, int npoint,
+            const int32_t *start_idx /* nullable */, int skip_origin, int32_t *idx_out, void *stream);
+/*
+ * Ball query: replaces query_ball_point(radius, nsample, xyz, new_xyz) (models/pointnet2_utils.py:93-113): for every
+ * centroid the first `nsample` point indices (ascending) with squared distance <= radius2, padded with the first
+ * hit; N when nothing is inside.  group_idx: int32 (B, S, nsample).  radius2 = (float)(radius**2).
+ */
+PCL_API int pcl_ball_query(const void *xyz, int dtype, int64_t bs, int64_t rs,
+                   const void *new_xyz, int ndtype, int64_t nbs, int64_t nrs,
+                   int B, int N, int S, float radius2, int nsample, int32_t *group_idx, void *stream);
+
 /* ------------------------------------------------------------------ host-buffer entry points -------------- */
 /*
  * End-to-end calls with HOST buffers (what a non-torch caller binds; also bench.py's e2e leg).

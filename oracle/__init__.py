@@ -26,7 +26,7 @@ _f64p = ctypes.POINTER(ctypes.c_double)
 
 
 def build(force: bool = False) -> str:
-    srcs = [os.path.join(_HERE, f) for f in ("emd_oracle.c", "chamfer_oracle.c", "Makefile")]
+    srcs = [os.path.join(_HERE, f) for f in ("emd_oracle.c", "chamfer_oracle.c", "fps_oracle.c", "Makefile")]
     have_src = all(os.path.exists(s) for s in srcs)
     stale = (not os.path.exists(_SO)) or (have_src and any(os.path.getmtime(s) > os.path.getmtime(_SO) for s in srcs))
     if force or stale:
@@ -43,6 +43,7 @@ def lib():
         _lib.emd_oracle_backward.restype = ctypes.c_int
         _lib.chamfer_oracle_forward.restype = ctypes.c_int
         _lib.chamfer_oracle_backward.restype = ctypes.c_int
+        _lib.fps_oracle.restype = ctypes.c_int
     return _lib
 
 
@@ -174,3 +175,38 @@ def chamfer_backward(x, y, idx_x, idx_y, g=1.0, x_lengths=None, y_lengths=None):
         ctypes.c_float(g), _ptr(gx, _f32p), _ptr(gy, _f32p))
     assert rc == 0
     return gx, gy
+
+
+def fps(xyz, npoint, start=None, skip_origin=False):
+    """farthest_point_sample(xyz, npoint) (models/pointnet2_utils.py:89-90) -> int32 (B, npoint); see fps_oracle.c."""
+    x = _np32(xyz)
+    b, n, _ = x.shape
+    idx = np.zeros((b, npoint), np.int32)
+    st = None if start is None else np.ascontiguousarray(np.asarray(start, dtype=np.int32))
+    rc = lib().fps_oracle(_ptr(x, _f32p), ctypes.c_long(x.strides[0] // 4), ctypes.c_long(x.strides[1] // 4), ctypes.c_int(b),
+                          ctypes.c_int(n), ctypes.c_int(npoint), _ptr(st, _i32p) if st is not None else None,
+                          ctypes.c_int(1 if skip_origin else 0), _ptr(idx, _i32p))
+    assert rc == 0
+    return idx
+
+
+def ball_query(radius, nsample, xyz, new_xyz):
+    """query_ball_point (models/pointnet2_utils.py:93-113) restated with the difference-form squared distance
+    ((dx*dx + dy*dy) + dz*dz in fp32; the reference uses the matmul expansion, which differs by ~1e-7 absolute, so
+    parity with it is exact except for points that close to the sphere -- tests/golden marks those centroids)."""
+    x, c = _np32(xyz), _np32(new_xyz)
+    b, n, _ = x.shape
+    s = c.shape[1]
+    r2 = np.float32(radius ** 2)
+    out = np.empty((b, s, nsample), np.int32)
+    for i in range(b):
+        d = c[i][:, None, :3] - x[i][None, :, :3]                      # (s, n, 3) fp32
+        d2 = (d[..., 0] * d[..., 0] + d[..., 1] * d[..., 1]) + d[..., 2] * d[..., 2]
+        inside = ~(d2 > r2)
+        for q in range(s):
+            hits = np.nonzero(inside[q])[0]
+            first = hits[0] if len(hits) else n
+            row = np.full(nsample, first, np.int32)
+            row[: min(len(hits), nsample)] = hits[:nsample]
+            out[i, q] = row
+    return out

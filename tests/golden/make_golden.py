@@ -152,6 +152,27 @@ def main():
     loss.backward()
     out.update(ch6_pred=p6.detach().numpy(), ch6_target=t6.numpy(), ch6_loss=np.float32(loss.item()), ch6_grad=p6.grad.numpy())
 
+    # (6) ball query + sample_and_group through the REAL reference torch code (models/pointnet2_utils.py:93-144);
+    #     its FPS is third-party CUDA (pointnet2_ops), stubbed with the CPU oracle of the commented torch algorithm.
+    p2o = types.ModuleType("pointnet2_ops")
+    p2u = types.ModuleType("pointnet2_ops.pointnet2_utils")
+    p2u.furthest_point_sample = lambda xyz, npoint: torch.from_numpy(oracle.fps(xyz, npoint))
+    p2o.pointnet2_utils = p2u
+    sys.modules.update({"pointnet2_ops": p2o, "pointnet2_ops.pointnet2_utils": p2u})
+    import pointcloud_vision.models.pointnet2_utils as ref_p2
+    _, t4 = synth.table_clouds(2, 1024, seed=16)
+    xyz = t4[:, :, :3].contiguous()
+    fps_idx = ref_p2.farthest_point_sample(xyz, 128)
+    new_xyz = ref_p2.index_points(xyz, fps_idx)
+    out.update(bq_xyz=xyz.numpy(), bq_fps_idx=fps_idx.numpy().astype(np.int32), bq_new_xyz=new_xyz.numpy())
+    sq = ref_p2.square_distance(new_xyz, xyz)  # the reference's matmul form: |x|^2 + |y|^2 - 2 x.y, abs error ~3e-7 here
+    for name, radius, nsample in (("a", 0.1, 16), ("b", 0.2, 32), ("c", 0.02, 8)):
+        gi = ref_p2.query_ball_point(radius, nsample, xyz, new_xyz)
+        out[f"bq_{name}_idx"] = gi.numpy().astype(np.int32)
+        out[f"bq_{name}_params"] = np.array([radius, nsample], np.float64)
+        # centroids with a point so close to the sphere that the matmul form and the difference form may disagree
+        out[f"bq_{name}_ambiguous"] = ((sq - radius ** 2).abs() <= 2e-6).any(-1).numpy()
+
     path = os.path.join(ROOT, "tests", "golden", "loss_golden.npz")
     np.savez_compressed(path, **out)
     print("wrote", path, os.path.getsize(path), "bytes")
