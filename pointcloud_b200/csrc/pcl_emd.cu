@@ -41,7 +41,7 @@ constexpr int EMD_WARPS = EMD_THREADS / 32;
 constexpr int EMD_MAX_N = 8192;      // 4097..8192: the cold half of the state lives in a per-CTA global-memory region (L2)
 constexpr int EMD_SMEM_ONLY_N = 4096;  // up to here the whole auction state fits into shared memory
 constexpr int TILE = 32;  // targets per spatial tile (one bounding box per tile)
-constexpr int EMD_WPB_MAX = 4 * EMD_WARPS;  // at most this many bidders per CTA: warp-per-bidder scan
+constexpr int EMD_WPB_MAX = 8 * EMD_WARPS;  // at most this many bidders per CTA: warp-per-bidder scan
 constexpr unsigned short NONE16 = 0xffffu;
 constexpr unsigned NOLAST = 0xffffffffu;
 constexpr float FILTER_MARGIN = 2e-6f;  // > 4.2e-7 worst-case rounding slack of the filter
@@ -124,8 +124,20 @@ __device__ __forceinline__ float bid_value_exact(float s, float price) {
     return __double2float_rn(__dsub_rn(__dsub_rn(3.0, (double)__fsqrt_rn(s)), (double)price));
 }
 
-// 18-bit Morton code of a point (6 bits per axis over [0,1]); only the spatial coherence of the internal
-// order depends on it, never a result.
+// 12-bit Morton cell of a point (4 bits per axis over [0,1]); only the spatial coherence of the internal order
+// depends on it, never a result.
+__device__ __forceinline__ unsigned spread4(unsigned v) {
+    v = (v | (v << 4)) & 0x0C3u;
+    v = (v | (v << 2)) & 0x249u;
+    return v;
+}
+__device__ __forceinline__ unsigned morton12(float3 p) {
+    const unsigned qx = (unsigned)min(max((int)(p.x * 16.f), 0), 15), qy = (unsigned)min(max((int)(p.y * 16.f), 0), 15),
+                   qz = (unsigned)min(max((int)(p.z * 16.f), 0), 15);
+    return spread4(qx) | (spread4(qy) << 1) | (spread4(qz) << 2);
+}
+constexpr int EMD_CELLS = 4096;
+// 18-bit Morton key (6 bits per axis); its top 12 bits are the cell above, so ordering by (cell, key) == ordering by key
 __device__ __forceinline__ unsigned spread6(unsigned v) {
     v = (v | (v << 8)) & 0x0000300Fu;
     v = (v | (v << 4)) & 0x000030C3u;
@@ -136,21 +148,6 @@ __device__ __forceinline__ unsigned morton18(float3 p) {
     const unsigned qx = (unsigned)min(max((int)(p.x * 64.f), 0), 63), qy = (unsigned)min(max((int)(p.y * 64.f), 0), 63),
                    qz = (unsigned)min(max((int)(p.z * 64.f), 0), 63);
     return spread6(qx) | (spread6(qy) << 1) | (spread6(qz) << 2);
-}
-
-// in-place ascending bitonic sort of np (power of two) unique 32-bit keys in shared memory, whole CTA
-__device__ inline void bitonic_sort(unsigned *keys, int np) {
-    for (int k = 2; k <= np; k <<= 1) {
-        for (int j = k >> 1; j > 0; j >>= 1) {
-            for (int i = threadIdx.x; i < (np >> 1); i += EMD_THREADS) {
-                const int lo = ((i & ~(j - 1)) << 1) | (i & (j - 1)), hi = lo | j;
-                const unsigned a = keys[lo], b = keys[hi];
-                const bool up = ((lo & k) == 0);
-                if ((a > b) == up) { keys[lo] = b; keys[hi] = a; }
-            }
-            __syncthreads();
-        }
-    }
 }
 
 struct Top2 {
@@ -249,20 +246,54 @@ emd_auction_kernel(Pts xyz1, Pts xyz2, int N, float eps, int iters, int flags, i
     // ---- init: internal (Morton) order of both clouds, tiles, auction state (emd_module.py:45-56) ----------
     if (tid == 0) *S.evals = 0ull;
     if (flags & EMD_F_SORT) {
-        unsigned *keys = reinterpret_cast<unsigned *>(S.pub);  // 16N bytes of scratch >= 4 * np
-        int np = 1;
-        while (np < N) np <<= 1;
+        // Counting sort by Morton cell (histogram with shared-memory atomics, block scan, scatter, in-cell ranking).
+        // Every tie rule uses original indices, so results never depend on the internal order (the parity tests run it
+        // sorted, in natural order and with N > 4096); it only has to be the SAME order in all CTAs of a cluster.
+        int *hist = reinterpret_cast<int *>(S.pub);     // 16 KB of scratch (pub holds 16 N >= 16 KB for N >= 1024)
+        unsigned short *rnk = S.unass;                  // rank of every point inside its cell
         for (int pass = 0; pass < 2; pass++) {  // 0: targets, 1: predictions
             const Pts &src = pass ? xyz1 : xyz2;
-            for (int k = tid; k < np; k += T)
-                keys[k] = (k < N) ? ((morton18(ld_xyz(src, cloud, k)) << 12) | (unsigned)k) : 0xffffffffu;
+            for (int c = tid; c < EMD_CELLS; c += T) hist[c] = 0;
             __syncthreads();
-            bitonic_sort(keys, np);
+            for (int k = tid; k < N; k += T) rnk[k] = (unsigned short)atomicAdd(&hist[morton12(ld_xyz(src, cloud, k))], 1);
+            __syncthreads();
+            {   // exclusive prefix sum over the cells: 8 consecutive cells per thread + block scan
+                constexpr int CPT = EMD_CELLS / EMD_THREADS;
+                int v[CPT], sum = 0;
+#pragma unroll
+                for (int i = 0; i < CPT; i++) { v[i] = hist[tid * CPT + i]; sum += v[i]; }
+                int incl2 = sum;
+#pragma unroll
+                for (int o = 1; o < 32; o <<= 1) {
+                    const int u = __shfl_up_sync(0xffffffffu, incl2, o);
+                    if (lane >= o) incl2 += u;
+                }
+                if (lane == 31) S.wsum[wid] = incl2;
+                __syncthreads();
+                int base = incl2 - sum;
+                for (int w = 0; w < wid; w++) base += S.wsum[w];
+#pragma unroll
+                for (int i = 0; i < CPT; i++) { hist[tid * CPT + i] = base; base += v[i]; }
+            }
+            __syncthreads();
+            // scatter (fine key | original index) in arrival order, then rank every point among its cell mates by that
+            // unique key: the final internal order is the full Morton order, a deterministic function of the input and
+            // hence identical in every CTA of the cluster (the replicas exchange internal indices)
+            unsigned *tmp = S.last;
             for (int k = tid; k < N; k += T) {
-                const int orig = (int)(keys[k] & 0xfffu);
-                const float3 p = ld_xyz(src, cloud, orig);
-                if (pass == 0) { S.tperm[k] = (unsigned short)orig; S.tgt[k] = make_float4(p.x, p.y, p.z, 3.0f); }
-                else { S.pperm[k] = (unsigned short)orig; if (S.x1) S.x1[k] = make_float4(p.x, p.y, p.z, 0.f); }
+                const float3 p = ld_xyz(src, cloud, k);
+                tmp[hist[morton12(p)] + (int)rnk[k]] = (morton18(p) << 12) | (unsigned)k;
+            }
+            __syncthreads();
+            for (int k = tid; k < N; k += T) {
+                const float3 p = ld_xyz(src, cloud, k);
+                const int cell = (int)morton12(p);
+                const unsigned key = (morton18(p) << 12) | (unsigned)k;
+                const int lo = hist[cell], hi = (cell + 1 < EMD_CELLS) ? hist[cell + 1] : N;
+                int pos = lo;
+                for (int q = lo; q < hi; q++) pos += (tmp[q] < key) ? 1 : 0;
+                if (pass == 0) { S.tperm[pos] = (unsigned short)k; S.tgt[pos] = make_float4(p.x, p.y, p.z, 3.0f); }
+                else { S.pperm[pos] = (unsigned short)k; if (S.x1) S.x1[pos] = make_float4(p.x, p.y, p.z, 0.f); }
             }
             __syncthreads();
         }
@@ -815,7 +846,7 @@ extern "C" int pcl_emd_fwd(const void *xyz1, int dtype1, int64_t bs1, int64_t rs
             return PCL_E_WORKSPACE;
         }
     }
-    if (N <= EMD_SMEM_ONLY_N && emd_smem_bytes(N, EMD_F_SORT) <= (size_t)di.max_smem_optin) flags |= EMD_F_SORT;
+    if (N >= 1024 && N <= EMD_SMEM_ONLY_N && emd_smem_bytes(N, EMD_F_SORT) <= (size_t)di.max_smem_optin) flags |= EMD_F_SORT;
     if (N <= EMD_SMEM_ONLY_N && emd_smem_bytes(N, flags | EMD_F_X1) <= (size_t)di.max_smem_optin) flags |= EMD_F_X1;
     if (getenv("PCL_EMD_NO_SORT")) flags &= ~EMD_F_SORT;  // development aid: natural order (no spatial pruning benefit)
     int pcap = 4 * EMD_THREADS;  // room for 64 work items with partials; fall back to 16 when shared memory is tight
