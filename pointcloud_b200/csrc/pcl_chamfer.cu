@@ -19,7 +19,7 @@ namespace {
 
 constexpr int CH_THREADS = 128;
 constexpr int CH_TILE = 1024;  // targets per shared-memory tile (16 KB)
-constexpr int CH_CHUNK = 64;   // argmin recovery granularity
+constexpr int CH_CHUNK = 32;   // argmin recovery granularity
 
 template <bool FMA>
 __device__ __forceinline__ float sqdist3(float qx, float qy, float qz, const float4 &t) {
@@ -107,10 +107,17 @@ chamfer_nn3_kernel(Pts x, const int64_t *__restrict__ x_len, Pts y, const int64_
             }
 #pragma unroll
             for (int r = 0; r < QPT; r++) {
-                if (improved[r]) {  // the tile is still in shared memory: find the first index that attains the minimum
+                if (improved[r]) {  // the tile is still in shared memory: find the lowest index that attains the minimum
+                    // Every lane re-scans a DIFFERENT chunk; chunks are 1 KB apart, i.e. the same banks.  Rotating the
+                    // start by the lane id makes the 32 LDS.128 of a step hit 32 consecutive float4 (conflict-free).
                     const int c0 = bchunk[r], c1 = min(c0 + CH_CHUNK, cnt);
-                    for (int j = c1 - 1; j >= c0; j--)
-                        if (sqdist3<FMA>(qx[r], qy[r], qz[r], tile[j]) == best[r]) bi[r] = t0 + j;
+                    int found = 0x7fffffff;
+#pragma unroll 4
+                    for (int jj = 0; jj < CH_CHUNK; jj++) {
+                        const int j = c0 + ((jj + (int)threadIdx.x) & (CH_CHUNK - 1));
+                        if (j < c1 && sqdist3<FMA>(qx[r], qy[r], qz[r], tile[j]) == best[r]) found = min(found, j);
+                    }
+                    bi[r] = t0 + found;
                     improved[r] = false;
                 }
             }
