@@ -41,7 +41,7 @@ constexpr int EMD_WARPS = EMD_THREADS / 32;
 constexpr int EMD_MAX_N = 8192;      // 4097..8192: the cold half of the state lives in a per-CTA global-memory region (L2)
 constexpr int EMD_SMEM_ONLY_N = 4096;  // up to here the whole auction state fits into shared memory
 constexpr int TILE = 32;  // targets per spatial tile (one bounding box per tile)
-constexpr int EMD_WPB_MAX = 8 * EMD_WARPS;  // at most this many bidders per CTA: warp-per-bidder scan
+constexpr int EMD_WPB_MAX = 6 * EMD_WARPS;  // at most this many bidders per CTA: warp-per-bidder scan (swept on config 2: 48..128)
 constexpr unsigned short NONE16 = 0xffffu;
 constexpr unsigned NOLAST = 0xffffffffu;
 constexpr float FILTER_MARGIN = 2e-6f;  // > 4.2e-7 worst-case rounding slack of the filter
@@ -222,7 +222,7 @@ __device__ __forceinline__ Top2 top2_init(const EmdSmem &S, unsigned lastpack, i
 // reached through the PCL_EMD_PROFILE environment variable; the product path instantiates PROF=false).
 template <bool PROF>
 __global__ void __launch_bounds__(EMD_THREADS, 1)
-emd_auction_kernel(Pts xyz1, Pts xyz2, int N, float eps, int iters, int flags, int pcap, float *__restrict__ dist,
+emd_auction_kernel(Pts xyz1, Pts xyz2, int N, float eps, int iters, int flags, int pcap, int wpb_max, float *__restrict__ dist,
                    int *__restrict__ assignment, int *__restrict__ stats, long long *__restrict__ prof,
                    unsigned char *__restrict__ cold_ws) {
     long long pt[8] = {0, 0, 0, 0, 0, 0, 0, 0}, pc = 0;
@@ -404,7 +404,7 @@ emd_auction_kernel(Pts xyz1, Pts xyz2, int N, float eps, int iters, int flags, i
         // The (spatially sorted) list is dealt to the CTAs of the cluster in an interleaved way -- single bidders when
         // there are few (warp-per-bidder mode), blocks of 32 neighbours otherwise -- so that every CTA sees the
         // same mix of easy and hard regions.  list position of local bidder b:  pos(b).
-        const bool wpb = (U > 0 && (U + cs - 1) / cs <= EMD_WPB_MAX);
+        const bool wpb = (U > 0 && (U + cs - 1) / cs <= wpb_max);
         const int gsz = wpb ? 1 : 32;                       // dealing granularity
         const int nblk = (U + gsz - 1) / gsz;               // blocks in the list
         const int myblk = (nblk > rank) ? (nblk - rank + cs - 1) / cs : 0;  // blocks rank, rank+cs, ...
@@ -852,6 +852,8 @@ extern "C" int pcl_emd_fwd(const void *xyz1, int dtype1, int64_t bs1, int64_t rs
     int pcap = 4 * EMD_THREADS;  // room for 64 work items with partials; fall back to 16 when shared memory is tight
     if (emd_smem_bytes(N, flags, pcap) > (size_t)di.max_smem_optin) pcap = EMD_THREADS;
     const size_t smem = emd_smem_bytes(N, flags, pcap);
+    int wpb_max = EMD_WPB_MAX;
+    if (const char *e = getenv("PCL_EMD_WPB")) wpb_max = atoi(e);  // development aid
     if (smem > (size_t)di.max_smem_optin) { set_error("emd_fwd: N=%d needs %zu B shared memory (> %d)", N, smem, di.max_smem_optin); return PCL_E_UNSUPPORTED; }
     static thread_local int attr_dev = -1;
     int dev = 0;
@@ -874,9 +876,9 @@ extern "C" int pcl_emd_fwd(const void *xyz1, int dtype1, int64_t bs1, int64_t rs
     // development aid: PCL_EMD_PROFILE=1 makes the workspace receive per-phase clock totals (B*cs*8 int64)
     static const bool profile = getenv("PCL_EMD_PROFILE") != nullptr;
     if (profile && !(flags & EMD_F_COLD) && workspace && workspace_bytes >= ((size_t)B * cs * 8 + 512) * sizeof(long long)) {
-        PCL_CUDA(cudaLaunchKernelEx(&cfg, emd_auction_kernel<true>, p1, p2, N, eps, iters, flags, pcap, dist, (int *)assignment, (int *)stats, (long long *)workspace, (unsigned char *)nullptr));
+        PCL_CUDA(cudaLaunchKernelEx(&cfg, emd_auction_kernel<true>, p1, p2, N, eps, iters, flags, pcap, wpb_max, dist, (int *)assignment, (int *)stats, (long long *)workspace, (unsigned char *)nullptr));
     } else {
-        PCL_CUDA(cudaLaunchKernelEx(&cfg, emd_auction_kernel<false>, p1, p2, N, eps, iters, flags, pcap, dist, (int *)assignment, (int *)stats, (long long *)nullptr, (unsigned char *)((flags & EMD_F_COLD) ? workspace : nullptr)));
+        PCL_CUDA(cudaLaunchKernelEx(&cfg, emd_auction_kernel<false>, p1, p2, N, eps, iters, flags, pcap, wpb_max, dist, (int *)assignment, (int *)stats, (long long *)nullptr, (unsigned char *)((flags & EMD_F_COLD) ? workspace : nullptr)));
     }
     return PCL_OK;
 }
