@@ -120,7 +120,8 @@ def make_pool(torch, synth, device, rank, n_sets):
 
 class DeviceStep:
     """The hot path through the C ABI with preallocated outputs (no Python allocation in the timed region)."""
-    KERNELS_PER_STEP = 7  # chamfer_nn3, chamfer_finish, chamfer_bwd, emd_auction, wreduce_stage1, wreduce_stage2, emd_weighted_bwd
+    # fill2, chamfer_nn3, chamfer_finish, chamfer_bwd (side stream) | emd_auction, wreduce_stage1, wreduce_stage2, emd_weighted_bwd, emd_mean
+    KERNELS_PER_STEP = 9
 
     def __init__(self, torch, _lib, device):
         self.torch, self.lib, self.L = torch, _lib, _lib.lib()
@@ -134,6 +135,8 @@ class DeviceStep:
         self.sums, self.gemd = e(2), e(b, n, 3)
         self.cws = self.L.pcl_chamfer_workspace_bytes(b, n, n); self.cw = torch.empty(self.cws, device=device, dtype=torch.uint8)
         self.ews = self.L.pcl_emd_workspace_bytes(b, n); self.ew = torch.empty(self.ews, device=device, dtype=torch.uint8)
+        self.sws = self.L.pcl_chamfer_emd_step_scratch_bytes(b, n); self.sw = torch.empty(self.sws, device=device, dtype=torch.uint8)
+        self.losses = e(4)
 
     def chamfer(self, p, t, st):
         L, A, b, n = self.L, self.lib.pts_args, B_PER_GPU, NPTS
@@ -156,7 +159,10 @@ class DeviceStep:
         return rc
 
     def __call__(self, p, t, st):
-        rc = self.chamfer(p, t, st) | self.emd_fwd(p, t, st) | self.emd_rest(p, t, st)
+        """The whole step in ONE C-ABI call (pcl_chamfer_emd_step): Chamfer on the library's side stream next to the auction."""
+        A = self.lib.pts_args
+        rc = self.L.pcl_chamfer_emd_step(*A(p), *A(t), B_PER_GPU, NPTS, EPS, ITERS, 0, self.losses.data_ptr(), self.gx.data_ptr(),
+                                         self.gemd.data_ptr(), self.sw.data_ptr(), self.sws, st)
         if rc:
             raise RuntimeError(self.L.pcl_last_error().decode())
 
@@ -284,17 +290,26 @@ def main():
     ms_per_step = ms_total / K
     value = world * B_PER_GPU * K / (ms_total * 1e-3)
 
-    # ---- per-kernel breakdown on rank 0's stream (explains `value`; same inputs, events around each phase) ----
+    # ---- per-kernel breakdown on rank 0's stream (explains `value`; same inputs, the phases run one after the other
+    #      here, whereas the timed step above overlaps Chamfer with the auction) ----
     phases = {"chamfer_fwd_bwd": [], "emd_fwd": [], "emd_reduce_bwd": []}
     per_regime = {"independent": [], "noisy": []}
-    sum_u, executed = [], []
+    sum_u, executed, seq_ms = [], [], []
     for i in range(min(K, 32)):
         p, t, regime = pool[(W + i) % n_sets]
         a, b_, c, d = ev(), ev(), ev(), ev()
         a.record(); step.chamfer(p, t, st); b_.record(); step.emd_fwd(p, t, st); c.record(); step.emd_rest(p, t, st); d.record()
         torch.cuda.synchronize()
+        per_regime_seq = a.elapsed_time(d)
         phases["chamfer_fwd_bwd"].append(a.elapsed_time(b_)); phases["emd_fwd"].append(b_.elapsed_time(c)); phases["emd_reduce_bwd"].append(c.elapsed_time(d))
-        per_regime[regime].append(a.elapsed_time(d))
+        e_a, e_b = ev(), ev()
+        e_a.record(); step(p, t, st); e_b.record()
+        torch.cuda.synchronize()
+        per_regime[regime].append(e_a.elapsed_time(e_b))
+        seq_ms.append(per_regime_seq)
+        if step.chamfer(p, t, st) | step.emd_fwd(p, t, st) | step.emd_rest(p, t, st):
+            raise RuntimeError(_lib.lib().pcl_last_error().decode())
+        torch.cuda.synchronize()
         sum_u.append(int(step.stats[:, 0].sum().item()))
         executed.append(int(((step.stats[:, 4].long() & 0xffffffff) + (step.stats[:, 5].long() << 32)).sum().item()))
     emd_ms = statistics.mean(phases["emd_fwd"])
@@ -321,6 +336,7 @@ def main():
     breakdown["ms_per_step_independent"] = statistics.mean(per_regime["independent"]) if per_regime["independent"] else None
     breakdown["ms_per_step_noisy"] = statistics.mean(per_regime["noisy"]) if per_regime["noisy"] else None
     breakdown["chamfer_directed_pair_evals_per_s"] = ch_evals / (breakdown["chamfer_fwd_bwd"] * 1e-3)
+    breakdown["ms_per_step_phases_run_sequentially"] = statistics.mean(seq_ms)
 
     # ---- e2e: HOST buffers in, HOST results out, every step, through the C ABI (pcl_chamfer_emd_step_host) ------
     # timed region per step: H2D of that step's pinned inputs, all 7 kernels, D2H of the three loss scalars, stream sync

@@ -168,6 +168,21 @@ PCL_API int pcl_ball_query(const void *xyz, int dtype, int64_t bs, int64_t rs,
                    const void *new_xyz, int ndtype, int64_t nbs, int64_t nrs,
                    int B, int N, int S, float radius2, int nsample, int32_t *group_idx, void *stream);
 
+/* ------------------------------------------------------------------ composite step ------------------------ */
+/*
+ * One pass of the whole hot path over a batch that is already on the device: Chamfer fwd+bwd (upstream gradient 1)
+ * and EMD fwd + sqrt-mean (utils.py:304, weights == 1) + bwd.  Chamfer is forked onto a library-owned side stream and
+ * runs next to the auction kernel (which leaves 20 of the 148 SMs and about half of the issue slots free); it is joined
+ * back into `stream` before the call's work completes.  losses: device float[3] = {chamfer_x, chamfer_y, EMD mean};
+ * grad_pred_chamfer / grad_pred_emd: device (B,N,3) fp32.
+ */
+PCL_API size_t pcl_chamfer_emd_step_scratch_bytes(int B, int N);
+PCL_API int pcl_chamfer_emd_step(const void *pred, int dtype1, int64_t bs1, int64_t rs1,
+                         const void *target, int dtype2, int64_t bs2, int64_t rs2,
+                         int B, int N, float eps, int iters, int chamfer_mode,
+                         float *losses, float *grad_pred_chamfer, float *grad_pred_emd,
+                         void *scratch, size_t scratch_bytes, void *stream);
+
 /* ------------------------------------------------------------------ host-buffer entry points -------------- */
 /*
  * End-to-end calls with HOST buffers (what a non-torch caller binds; also bench.py's e2e leg).

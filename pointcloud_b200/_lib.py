@@ -37,6 +37,8 @@ _SIGNATURES = {
     "pcl_fps_max_points": (c_int, []),
     "pcl_fps": (c_int, _PTS + [c_int, c_int, c_int, c_void_p, c_int, c_void_p, c_void_p]),
     "pcl_ball_query": (c_int, _PTS + _PTS + [c_int, c_int, c_int, c_float, c_int, c_void_p, c_void_p]),
+    "pcl_chamfer_emd_step_scratch_bytes": (c_size_t, [c_int, c_int]),
+    "pcl_chamfer_emd_step": (c_int, _PTS + _PTS + [c_int, c_int, c_float, c_int, c_int] + [c_void_p] * 3 + [c_void_p, c_size_t, c_void_p]),
     "pcl_loss_host_scratch_bytes": (c_size_t, [c_int, c_int]),
     "pcl_chamfer_emd_step_host": (c_int, [c_void_p, c_void_p, c_int, c_int, c_float, c_int, c_int] + [c_void_p] * 3 + [c_void_p, c_size_t, c_void_p]),
 }

@@ -66,26 +66,109 @@ extern "C" int pcl_device_info(int *sm_count, int *cc_major, int *cc_minor, int 
     return PCL_OK;
 }
 
-// ---- host-buffer composite step ---------------------------------------------------------------------------
+// ---- composite step: Chamfer fwd+bwd and EMD fwd+bwd of one batch, device or host buffers ------------------------
 namespace {
-struct HostStepLayout {
-    size_t pred, target, dist_x, idx_x, dist_y, idx_y, grad_x, grad_y, emd_dist, emd_asg, grad_emd, scalars, ch_ws, emd_ws, total;
+struct StepLayout {
+    size_t dist_x, idx_x, dist_y, idx_y, grad_y, emd_dist, emd_asg, scalars, ch_ws, emd_ws, total;
 };
-HostStepLayout host_layout(int B, int N) {
-    HostStepLayout L;
+StepLayout step_layout(int B, int N) {
+    StepLayout L;
     const size_t pts = align_up((size_t)B * N * 3 * sizeof(float), 256), per = align_up((size_t)B * N * 4, 256);
     size_t o = 0;
-    L.pred = o; o += pts;  L.target = o; o += pts;
     L.dist_x = o; o += per; L.idx_x = o; o += per; L.dist_y = o; o += per; L.idx_y = o; o += per;
-    L.grad_x = o; o += pts; L.grad_y = o; o += pts;
-    L.emd_dist = o; o += per; L.emd_asg = o; o += per; L.grad_emd = o; o += pts;
-    L.scalars = o; o += 256;  // [0..1] loss_xy, [2..3] emd sums, [4..5] ones, [6] emd mean
+    L.grad_y = o; o += pts;
+    L.emd_dist = o; o += per; L.emd_asg = o; o += per;
+    L.scalars = o; o += 256;  // [0..1] emd sums, [2..3] ones
     L.ch_ws = o; o += pcl_chamfer_workspace_bytes(B, N, N);
     L.emd_ws = o; o += pcl_emd_workspace_bytes(B, N);
     L.total = o;
     return L;
 }
+struct HostStepLayout {
+    size_t pred, target, grad_x, grad_emd, losses, step, total;
+};
+HostStepLayout host_layout(int B, int N) {
+    HostStepLayout L;
+    const size_t pts = align_up((size_t)B * N * 3 * sizeof(float), 256);
+    size_t o = 0;
+    L.pred = o; o += pts; L.target = o; o += pts; L.grad_x = o; o += pts; L.grad_emd = o; o += pts;
+    L.losses = o; o += 256;
+    L.step = o; o += step_layout(B, N).total;
+    L.total = o;
+    return L;
+}
+// Library-owned side stream: Chamfer runs next to the auction (which occupies 128 of the 148 SMs at ~45 % issue
+// utilisation and leaves shared memory / registers for a few more CTAs per SM), joined before the call returns control
+// of `stream` to the caller's next operation.
+struct SideStream {
+    int dev = -1;
+    cudaStream_t side = nullptr;
+    cudaEvent_t fork = nullptr, join = nullptr;
+};
+int side_stream(SideStream **out) {
+    static thread_local SideStream ss;
+    int dev = 0;
+    PCL_CUDA(cudaGetDevice(&dev));
+    if (ss.dev != dev) {
+        if (ss.side) { cudaStreamDestroy(ss.side); cudaEventDestroy(ss.fork); cudaEventDestroy(ss.join); ss = SideStream(); }
+        PCL_CUDA(cudaStreamCreateWithFlags(&ss.side, cudaStreamNonBlocking));
+        PCL_CUDA(cudaEventCreateWithFlags(&ss.fork, cudaEventDisableTiming));
+        PCL_CUDA(cudaEventCreateWithFlags(&ss.join, cudaEventDisableTiming));
+        ss.dev = dev;
+    }
+    *out = &ss;
+    return PCL_OK;
+}
 }  // namespace
+
+extern "C" size_t pcl_chamfer_emd_step_scratch_bytes(int B, int N) {
+    if (B < 0 || N < 0) return 0;
+    return step_layout(B, N).total;
+}
+
+extern "C" int pcl_chamfer_emd_step(const void *pred, int dtype1, int64_t bs1, int64_t rs1, const void *target, int dtype2,
+                                    int64_t bs2, int64_t rs2, int B, int N, float eps, int iters, int chamfer_mode,
+                                    float *losses, float *grad_pred_chamfer, float *grad_pred_emd, void *scratch,
+                                    size_t scratch_bytes, void *stream) {
+    if (B < 1 || N < 1) { set_error("step: bad size B=%d N=%d", B, N); return PCL_E_SHAPE; }
+    if (!pred || !target || !losses || !grad_pred_chamfer || !grad_pred_emd || !scratch) { set_error("step: null argument"); return PCL_E_ARG; }
+    const StepLayout L = step_layout(B, N);
+    if (scratch_bytes < L.total) { set_error("step: scratch too small (%zu < %zu)", scratch_bytes, L.total); return PCL_E_WORKSPACE; }
+    cudaStream_t st = (cudaStream_t)stream;
+    SideStream *ss = nullptr;
+    int rc = side_stream(&ss);
+    if (rc) return rc;
+    unsigned char *d = (unsigned char *)scratch;
+    float *sc = (float *)(d + L.scalars);
+    fill2_kernel<<<1, 1, 0, st>>>(sc + 2, 1.0f);
+    PCL_CUDA(cudaEventRecord(ss->fork, st));
+    PCL_CUDA(cudaStreamWaitEvent(ss->side, ss->fork, 0));
+    // caller's stream first: the auction kernel takes its 128 SMs (one 512-thread CTA each) right away ...
+    rc = pcl_emd_fwd(pred, dtype1, bs1, rs1, target, dtype2, bs2, rs2, B, N, eps, iters, (float *)(d + L.emd_dist),
+                     (int32_t *)(d + L.emd_asg), nullptr, d + L.emd_ws, pcl_emd_workspace_bytes(B, N), stream);
+    if (rc) return rc;
+    // ... then the side stream: Chamfer forward + backward (upstream gradient 1) fill the remaining SMs and the spare
+    // registers / shared memory / issue slots next to the auction CTAs
+    rc = pcl_chamfer_fwd(pred, dtype1, bs1, rs1, nullptr, target, dtype2, bs2, rs2, nullptr, B, N, N, 3, chamfer_mode,
+                         (float *)(d + L.dist_x), (int32_t *)(d + L.idx_x), (float *)(d + L.dist_y), (int32_t *)(d + L.idx_y),
+                         losses, d + L.ch_ws, pcl_chamfer_workspace_bytes(B, N, N), ss->side);
+    if (rc) return rc;
+    rc = pcl_chamfer_bwd(pred, dtype1, bs1, rs1, nullptr, target, dtype2, bs2, rs2, nullptr, B, N, N, 3, (int32_t *)(d + L.idx_x),
+                         (int32_t *)(d + L.idx_y), sc + 2, grad_pred_chamfer, (float *)(d + L.grad_y), ss->side);
+    if (rc) return rc;
+    PCL_CUDA(cudaEventRecord(ss->join, ss->side));
+    // caller's stream: mean sqrt(dist) (utils.py:304 with weights == 1) and the EMD backward
+    rc = pcl_emd_weighted_reduce((float *)(d + L.emd_dist), nullptr, nullptr, B, N, 0, sc + 0, d + L.emd_ws,
+                                 pcl_emd_workspace_bytes(B, N), stream);
+    if (rc) return rc;
+    rc = pcl_emd_weighted_bwd(pred, dtype1, bs1, rs1, target, dtype2, bs2, rs2, B, N, (int32_t *)(d + L.emd_asg),
+                              (float *)(d + L.emd_dist), nullptr, nullptr, 0, sc + 0, sc + 2, grad_pred_emd, stream);
+    if (rc) return rc;
+    emd_mean_kernel<<<1, 1, 0, st>>>(sc + 0, losses + 2);
+    PCL_CUDA(cudaGetLastError());
+    PCL_CUDA(cudaStreamWaitEvent(st, ss->join, 0));
+    return PCL_OK;
+}
 
 extern "C" size_t pcl_loss_host_scratch_bytes(int B, int N) {
     if (B < 0 || N < 0) return 0;
@@ -102,39 +185,16 @@ extern "C" int pcl_chamfer_emd_step_host(const float *pred_host, const float *ta
     if (dev_scratch_bytes < L.total) { set_error("step_host: scratch too small (%zu < %zu)", dev_scratch_bytes, L.total); return PCL_E_WORKSPACE; }
     cudaStream_t st = (cudaStream_t)stream;
     unsigned char *d = (unsigned char *)dev_scratch;
-    float *pred = (float *)(d + L.pred), *target = (float *)(d + L.target);
-    float *sc = (float *)(d + L.scalars);
+    float *pred = (float *)(d + L.pred), *target = (float *)(d + L.target), *losses = (float *)(d + L.losses);
     const size_t bytes = (size_t)B * N * 3 * sizeof(float);
     PCL_CUDA(cudaMemcpyAsync(pred, pred_host, bytes, cudaMemcpyHostToDevice, st));
     PCL_CUDA(cudaMemcpyAsync(target, target_host, bytes, cudaMemcpyHostToDevice, st));
-    fill2_kernel<<<1, 1, 0, st>>>(sc + 4, 1.0f);
     const int64_t bs = (int64_t)N * 3, rs = 3;
-    int rc;
-    // Chamfer forward + backward (upstream gradient 1)
-    rc = pcl_chamfer_fwd(pred, PCL_F32, bs, rs, nullptr, target, PCL_F32, bs, rs, nullptr, B, N, N, 3, chamfer_mode,
-                         (float *)(d + L.dist_x), (int32_t *)(d + L.idx_x), (float *)(d + L.dist_y),
-                         (int32_t *)(d + L.idx_y), sc + 0, d + L.ch_ws, pcl_chamfer_workspace_bytes(B, N, N), stream);
+    int rc = pcl_chamfer_emd_step(pred, PCL_F32, bs, rs, target, PCL_F32, bs, rs, B, N, eps, iters, chamfer_mode, losses,
+                                  (float *)(d + L.grad_x), (float *)(d + L.grad_emd), d + L.step, step_layout(B, N).total, stream);
     if (rc) return rc;
-    rc = pcl_chamfer_bwd(pred, PCL_F32, bs, rs, nullptr, target, PCL_F32, bs, rs, nullptr, B, N, N, 3,
-                         (int32_t *)(d + L.idx_x), (int32_t *)(d + L.idx_y), sc + 4, (float *)(d + L.grad_x),
-                         (float *)(d + L.grad_y), stream);
-    if (rc) return rc;
-    // EMD forward, mean sqrt(dist) (utils.py:304 with weights == 1), backward
-    rc = pcl_emd_fwd(pred, PCL_F32, bs, rs, target, PCL_F32, bs, rs, B, N, eps, iters, (float *)(d + L.emd_dist),
-                     (int32_t *)(d + L.emd_asg), nullptr, d + L.emd_ws, pcl_emd_workspace_bytes(B, N), stream);
-    if (rc) return rc;
-    rc = pcl_emd_weighted_reduce((float *)(d + L.emd_dist), nullptr, nullptr, B, N, 0, sc + 2, d + L.emd_ws,
-                                 pcl_emd_workspace_bytes(B, N), stream);
-    if (rc) return rc;
-    rc = pcl_emd_weighted_bwd(pred, PCL_F32, bs, rs, target, PCL_F32, bs, rs, B, N, (int32_t *)(d + L.emd_asg),
-                              (float *)(d + L.emd_dist), nullptr, nullptr, 0, sc + 2, sc + 4,
-                              (float *)(d + L.grad_emd), stream);
-    if (rc) return rc;
-    emd_mean_kernel<<<1, 1, 0, st>>>(sc + 2, sc + 6);
-    PCL_CUDA(cudaGetLastError());
-    // results back to the host: {chamfer_x, chamfer_y} and the EMD mean
-    PCL_CUDA(cudaMemcpyAsync(loss_host, sc + 0, 2 * sizeof(float), cudaMemcpyDeviceToHost, st));
-    PCL_CUDA(cudaMemcpyAsync(loss_host + 2, sc + 6, sizeof(float), cudaMemcpyDeviceToHost, st));
+    // results back to the host: {chamfer_x, chamfer_y, EMD mean}
+    PCL_CUDA(cudaMemcpyAsync(loss_host, losses, 3 * sizeof(float), cudaMemcpyDeviceToHost, st));
     if (grad_pred_chamfer_host) PCL_CUDA(cudaMemcpyAsync(grad_pred_chamfer_host, d + L.grad_x, bytes, cudaMemcpyDeviceToHost, st));
     if (grad_pred_emd_host) PCL_CUDA(cudaMemcpyAsync(grad_pred_emd_host, d + L.grad_emd, bytes, cudaMemcpyDeviceToHost, st));
     return PCL_OK;

@@ -150,6 +150,35 @@ def test_host_buffer_step_entry_point_matches_device_path():
     assert rc == -4 and b"scratch" in L.pcl_last_error()
 
 
+def test_composite_device_step_matches_separate_calls():
+    """pcl_chamfer_emd_step (Chamfer forked onto the library's side stream) == the separate entry points."""
+    from pointcloud_b200 import _lib
+    L = _lib.lib()
+    b, n = 6, 2048
+    pred, target = synth.autoencoder_batch(b, n, seed=21)
+    pc, tc = pred.cuda(), target.cuda()
+    px, tx = pc[:, :, :3], tc[:, :, :3]                         # strided views straight into the composite call
+    losses = torch.zeros(4, device="cuda")
+    gch, gem = torch.empty(b, n, 3, device="cuda"), torch.empty(b, n, 3, device="cuda")
+    nbytes = L.pcl_chamfer_emd_step_scratch_bytes(b, n)
+    scratch = torch.empty(nbytes, dtype=torch.uint8, device="cuda")
+    for _ in range(3):                                         # repeated calls reuse the side stream / events
+        rc = L.pcl_chamfer_emd_step(*_lib.pts_args(px), *_lib.pts_args(tx), b, n, 0.005, 50, 0, losses.data_ptr(), gch.data_ptr(),
+                                    gem.data_ptr(), scratch.data_ptr(), nbytes, torch.cuda.current_stream().cuda_stream)
+        assert rc == 0, L.pcl_last_error()
+    torch.cuda.synchronize()
+    xg = px.detach().clone().requires_grad_()
+    cl, _ = pcl.chamfer_distance(xg, tx)
+    cl.backward()
+    xe = px.detach().clone().requires_grad_()
+    dist, _ = pcl.emdModule()(xe, tx, 0.005, 50)
+    el = dist.sqrt().mean()
+    el.backward()
+    assert float(losses[0] + losses[1]) == pytest.approx(float(cl), rel=1e-6) and float(losses[2]) == pytest.approx(float(el), rel=1e-6)
+    np.testing.assert_allclose(npy(gch), npy(xg.grad), rtol=REL, atol=1e-9)
+    np.testing.assert_allclose(npy(gem), npy(xe.grad), rtol=REL, atol=1e-10)
+
+
 def test_sharded_wrapper_single_rank_is_identity():
     pred, target = synth.segmenter_batch(4, 1024, seed=2)
     p1, p2 = pred.cuda().requires_grad_(), pred.cuda().requires_grad_()
