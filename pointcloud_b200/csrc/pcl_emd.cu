@@ -5,10 +5,13 @@
 // persistent kernel.  A cloud is owned by a thread-block cluster of CS CTAs (CS in {1,2,4,8,16}, chosen so
 // that B*CS fills the 148 SMs).  Every CTA keeps the whole auction state of its cloud in shared memory
 // (targets, prices, assignment, inverse assignment) as a REPLICA:
+//   0. set-up: both clouds are put into an internal Morton order (counting sort), targets are cut into tiles of
+//      32 with a bounding box; every tie rule is evaluated on ORIGINAL indices, so the order never changes a result;
 //   1. every CTA compacts the list of unassigned bidders from its replica (identical in all CTAs);
-//   2. the bidders are split over the CTAs of the cluster; inside a CTA one thread scans one
-//      (bidder, target-chunk) item -- lanes of a warp share the chunk, so the target tile is read with
-//      broadcast LDS.128 -- and chunk partials are merged exactly like emd_cuda.cu:165-173;
+//   2. the bidders are dealt to the CTAs of the cluster and scanned through a dynamic work queue, either with one
+//      lane per bidder (a warp = 32 neighbouring bidders x a slice of tiles, broadcast LDS.128, whole tiles skipped
+//      when all 32 lanes prove them irrelevant) or, for few bidders, with one warp per bidder (32 boxes tested per
+//      ballot, one lane per target); slice partials are merged by a tree equivalent to emd_cuda.cu:165-173;
 //   3. finished bids (object, increment) are written into EVERY CTA's bid arrays through distributed
 //      shared memory, followed by the one cluster barrier of the iteration;
 //   4. every CTA resolves all bids redundantly (GetMax / Assign, emd_cuda.cu:181-215) on its replica with
@@ -21,11 +24,14 @@
 // for candidates that pass an exact-safe FP32 filter in the squared domain:
 //   skip k  <=>  s_k > (c_k - (T - margin))^2,  c_k = RU(3 - price_k) kept in the target tile's .w,
 // where T is a proven lower bound of the bidder's final second-best value (its running second best, seeded
-// with the exact current values of the two objects it preferred at its previous bid).  Skipped candidates
-// are strictly below the final second best, so best / second-best / first-argmax are exactly the
-// reference's (derivation in DESIGN.md "EMD filter").
+// with the exact current values of the two objects it preferred at its previous bid); a whole tile is skipped with
+// the same inequality on bounds (distance to the tile's box, tile maximum of c).  Skipped candidates are strictly
+// below the final second best, so best / second-best / argmax are exactly the reference's (derivation in DESIGN.md
+// "Why skipping is exact").
 // The reference's GetMax race (last writer wins inside a +-1e-6 window) is resolved as
 // "largest bidder index wins" (atomicMax), identical to oracle/emd_oracle.c.
+// Clouds of 4097..8192 points keep the hot half of the state (targets, prices) in shared memory and the cold half
+// (bids, per-object maxima, assignment arrays) in a per-CTA global-memory region.
 #include <cooperative_groups.h>
 #include <stdlib.h>
 
@@ -484,23 +490,31 @@ emd_auction_kernel(Pts xyz1, Pts xyz2, int N, float eps, int iters, int flags, i
                         }
                         if (lane == 0) my_evals += TILE * ((int)have[0] + (int)have[1] + (int)have[2] + (int)have[3]);
                         if (!__any_sync(0xffffffffu, any)) continue;
+                        // Every lane takes ITS first surviving slot, so that one pass through the sqrt/F2F/DADD chain serves
+                        // all lanes (a lane rarely has two survivors among its 4 targets; leftovers loop).
+                        do {
+                            int sel = -1;
 #pragma unroll
-                        for (int i = 0; i < 4; i++) {
-                            unsigned pm = __ballot_sync(0xffffffffu, pass[i]);
-                            if (!pm) continue;
-                            const int k = tix[i] * TILE + lane;
+                            for (int i = 3; i >= 0; i--) sel = pass[i] ? i : sel;
+                            float ssel = 0.f;
+                            int ksel = 0;
+#pragma unroll
+                            for (int i = 0; i < 4; i++) {
+                                if (sel == i) { ssel = sq[i]; ksel = tix[i] * TILE + lane; pass[i] = false; }
+                            }
                             float v = 0.f;
                             int ko = 0;
-                            if (pass[i]) { v = bid_value_exact(sq[i], S.pf[k]); ko = S.tperm ? (int)S.tperm[k] : k; }
+                            if (sel >= 0) { v = bid_value_exact(ssel, S.pf[ksel]); ko = S.tperm ? (int)S.tperm[ksel] : ksel; }
+                            unsigned pm = __ballot_sync(0xffffffffu, sel >= 0);
                             while (pm) {
                                 const int l = __ffs(pm) - 1;
                                 pm &= pm - 1;
                                 const float vl = __shfl_sync(0xffffffffu, v, l);
-                                const int kol = __shfl_sync(0xffffffffu, ko, l), kl = tix[i] * TILE + l;
+                                const int kol = __shfl_sync(0xffffffffu, ko, l), kl = __shfl_sync(0xffffffffu, ksel, l);
                                 if (vl > best || (vl == best && kol < bio)) { better = best; bi2 = bi; best = vl; bi = kl; bio = kol; }
                                 else if (vl > better) { better = vl; bi2 = kl; }
                             }
-                        }
+                        } while (__any_sync(0xffffffffu, pass[0] || pass[1] || pass[2] || pass[3]));
                         tm = fmaxf(tm, __fsub_rn(better, FILTER_MARGIN));
                     }
                 }
