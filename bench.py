@@ -331,7 +331,27 @@ def main():
                 "executed_fraction": statistics.mean(executed) / evals,
                 "executed_note": "algorithmic = every (bidder, target) pair of the reference's Bid (N * sum_t U_t); the kernel proves "
                                  "whole 32-target tiles irrelevant with an exact bounding-box test and really evaluates only this fraction"}
+    # secondary roofline: the Chamfer forward kernel alone (FP32 CUDA-core bound as well; unfused arithmetic => at most 50 % of
+    # the FLOP peak because 8 FLOP occupy 8 FMA-pipe issue slots; ncu FMA-pipe utilisation in profiles/r1_chamfer_variants.txt)
+    tch = []
+    for i in range(min(K, 32)):
+        p, t, _ = pool[(W + i) % n_sets]
+        a, b_ = ev(), ev()
+        a.record()
+        rc = step.L.pcl_chamfer_fwd(*_lib.pts_args(p), None, *_lib.pts_args(t), None, B_PER_GPU, NPTS, NPTS, 3, 0, step.dist_x.data_ptr(),
+                                    step.idx_x.data_ptr(), step.dist_y.data_ptr(), step.idx_y.data_ptr(), step.loss_xy.data_ptr(),
+                                    step.cw.data_ptr(), step.cws, st)
+        b_.record()
+        torch.cuda.synchronize()
+        assert rc == 0
+        tch.append(a.elapsed_time(b_))
     ch_evals = 2.0 * B_PER_GPU * NPTS * NPTS
+    ch_ms = statistics.mean(tch)
+    ch_achieved = FLOP_PER_CHAMFER_EVAL * ch_evals / (ch_ms * 1e-3) / 1e12
+    roofline_chamfer = {"kernel": "chamfer_nn3_kernel (+memset, finish)", "bound": "fp32-cuda-core", "achieved": ch_achieved, "peak": fp32_peak_tflops,
+                        "unit": "TFLOP/s", "frac": ch_achieved / fp32_peak_tflops, "traffic": None, "avg_launch_ms": ch_ms,
+                        "algorithmic": f"{FLOP_PER_CHAMFER_EVAL} FLOP x 2*B*N*M directed evaluations = {FLOP_PER_CHAMFER_EVAL * ch_evals:.3e} FLOP per launch",
+                        "fma_pipe_lane_ops_frac": 8 * ch_evals / (ch_ms * 1e-3) / (fp32_peak_tflops * 1e12 / 2)}
     breakdown = {k: statistics.mean(v) for k, v in phases.items()}
     breakdown["ms_per_step_independent"] = statistics.mean(per_regime["independent"]) if per_regime["independent"] else None
     breakdown["ms_per_step_noisy"] = statistics.mean(per_regime["noisy"]) if per_regime["noisy"] else None
@@ -430,6 +450,7 @@ def main():
                            "chamfer_mode": "unfused", "parallelism": f"batch-sharded x{world}, no data-path collective",
                            "l2": f"inputs rotate through {n_sets} sets = {n_sets * 2 * B_PER_GPU * NPTS * 12 / 1e6:.0f} MB > 126 MB L2 (no flush needed)"},
                 "clocks": clocks, "e2e": e2e, "gpu_launches": DeviceStep.KERNELS_PER_STEP * K, "roofline": roofline,
+                "roofline_chamfer": roofline_chamfer,
                 "cpu_baseline": cb, "breakdown_ms": breakdown, "reference_gpu": reference_gpu, "impl": "ours"}
         print(json.dumps(line))
     if world > 1:
