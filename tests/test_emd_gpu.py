@@ -41,6 +41,38 @@ def test_emd_forward_bit_exact_vs_oracle(kind, b, n, eps, iters):
     assert np.array_equal(st[:, 0], o["sum_unass"]) and np.array_equal(st[:, 1], o["iters_run"])
 
 
+@pytest.mark.parametrize("case", ["grid_ties", "all_pred_identical", "duplicate_targets", "out_of_range", "identical_clouds", "tiny_eps"])
+def test_emd_degenerate_inputs_bit_exact_vs_oracle(case, ref_ext):
+    """Exact ties everywhere: the order-independent tie rules (lowest original target index among equal values, largest
+    bidder index inside the GetMax window) must reproduce the oracle's sequential scan regardless of the internal
+    Morton order, the tile skipping and the scan mode."""
+    g = torch.Generator().manual_seed(7)
+    b, n, eps, iters = 3, 2048, 0.005, 50
+    x1, x2 = torch.rand(b, n, 3, generator=g), torch.rand(b, n, 3, generator=g)
+    if case == "grid_ties":            # coordinates on a coarse lattice: thousands of equal distances and equal values
+        x1 = torch.randint(0, 6, (b, n, 3), generator=g).float() / 6
+        x2 = torch.randint(0, 6, (b, n, 3), generator=g).float() / 6
+    elif case == "all_pred_identical":
+        x1 = torch.full((b, n, 3), 0.5)
+    elif case == "duplicate_targets":
+        x2 = x2[:, : n // 8].repeat(1, 8, 1)
+    elif case == "out_of_range":       # the reference assumes [0,1]^3 (emd_module.py:9); values may go negative outside
+        x1, x2 = x1 * 3 - 1, x2 * 4 - 2
+    elif case == "identical_clouds":
+        x1 = x2.clone()
+    elif case == "tiny_eps":
+        eps, iters = 1e-7, 30
+    o = oracle.emd_forward(x1, x2, eps, iters, nthreads=3)
+    d, a, st = pcl.emd_forward_raw(x1.cuda(), x2.cuda(), eps, iters, want_stats=True)
+    assert np.array_equal(npy(a), o["assignment"]) and np.array_equal(npy(d), o["dist"])
+    assert np.array_equal(npy(st)[:, 0], o["sum_unass"])
+    if ref_ext is not None:            # and the unmodified reference agrees wherever it is deterministic
+        rd, ra = ref_emd_forward(ref_ext, x1, x2, eps, iters)
+        for i in range(b):
+            if o["race_events"][i] == 0:
+                assert np.array_equal(npy(ra[i]), npy(a[i]))
+
+
 def test_emd_matches_unmodified_reference_extension(ref_ext):
     if ref_ext is None:
         pytest.skip("oracle/_ref/emd.so not built (needs /root/reference at build time)")
