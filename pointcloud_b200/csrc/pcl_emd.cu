@@ -228,7 +228,8 @@ __device__ __forceinline__ Top2 top2_init(const EmdSmem &S, unsigned lastpack, i
 // reached through the PCL_EMD_PROFILE environment variable; the product path instantiates PROF=false).
 template <bool PROF>
 __global__ void __launch_bounds__(EMD_THREADS, 1)
-emd_auction_kernel(Pts xyz1, Pts xyz2, int N, float eps, int iters, int flags, int pcap, int wpb_max, float *__restrict__ dist,
+emd_auction_kernel(Pts xyz1, Pts xyz2, int N, float eps, int iters, int flags, int pcap, int wpb_max, int items_target,
+                   float *__restrict__ dist,
                    int *__restrict__ assignment, int *__restrict__ stats, long long *__restrict__ prof,
                    unsigned char *__restrict__ cold_ws) {
     long long pt[8] = {0, 0, 0, 0, 0, 0, 0, 0}, pc = 0;
@@ -418,9 +419,9 @@ emd_auction_kernel(Pts xyz1, Pts xyz2, int N, float eps, int iters, int flags, i
         if (myblk > 0 && (rank + (myblk - 1) * cs) == nblk - 1) Uc -= nblk * gsz - U;  // the last block may be short
         auto pos = [&](int b) -> int { return ((b / gsz) * cs + rank) * gsz + (b % gsz); };
         const int Gn = (Uc + 31) >> 5;                                   // bidder groups (warps' worth)
-        // tile slices per group: aim at ~4 work items per warp (dynamic queue), bounded by the partial buffer
+        // tile slices per group: aim at ~2 work items per warp (dynamic queue), bounded by the partial buffer
         int KS = 1;
-        if (Gn > 0 && Gn < 4 * EMD_WARPS) KS = max(1, min(min((4 * EMD_WARPS + Gn - 1) / Gn, NT), pcap / (Gn * 32)));
+        if (Gn > 0 && Gn < items_target) KS = max(1, min(min((items_target + Gn - 1) / Gn, NT), pcap / (Gn * 32)));
         const int GS = Gn * 32;                                          // partial stride of one slice
         uint2 *pub_cur = S.pub + cur * n8;
 
@@ -863,11 +864,13 @@ extern "C" int pcl_emd_fwd(const void *xyz1, int dtype1, int64_t bs1, int64_t rs
     if (N >= 1024 && N <= EMD_SMEM_ONLY_N && emd_smem_bytes(N, EMD_F_SORT) <= (size_t)di.max_smem_optin) flags |= EMD_F_SORT;
     if (N <= EMD_SMEM_ONLY_N && emd_smem_bytes(N, flags | EMD_F_X1) <= (size_t)di.max_smem_optin) flags |= EMD_F_X1;
     if (getenv("PCL_EMD_NO_SORT")) flags &= ~EMD_F_SORT;  // development aid: natural order (no spatial pruning benefit)
-    int pcap = 4 * EMD_THREADS;  // room for 64 work items with partials; fall back to 16 when shared memory is tight
+    int pcap = 2 * EMD_THREADS;  // room for 32 work items with partials; fall back to 16 when shared memory is tight
     if (emd_smem_bytes(N, flags, pcap) > (size_t)di.max_smem_optin) pcap = EMD_THREADS;
     const size_t smem = emd_smem_bytes(N, flags, pcap);
     int wpb_max = EMD_WPB_MAX;
     if (const char *e = getenv("PCL_EMD_WPB")) wpb_max = atoi(e);  // development aid
+    int items_target = 2 * EMD_WARPS;  // work items per CTA and iteration in the lane-per-bidder mode (dynamic queue; swept 8..128 on config 2)
+    if (const char *e = getenv("PCL_EMD_ITEMS")) items_target = atoi(e);  // development aid
     if (smem > (size_t)di.max_smem_optin) { set_error("emd_fwd: N=%d needs %zu B shared memory (> %d)", N, smem, di.max_smem_optin); return PCL_E_UNSUPPORTED; }
     static thread_local int attr_dev = -1;
     int dev = 0;
@@ -890,9 +893,9 @@ extern "C" int pcl_emd_fwd(const void *xyz1, int dtype1, int64_t bs1, int64_t rs
     // development aid: PCL_EMD_PROFILE=1 makes the workspace receive per-phase clock totals (B*cs*8 int64)
     static const bool profile = getenv("PCL_EMD_PROFILE") != nullptr;
     if (profile && !(flags & EMD_F_COLD) && workspace && workspace_bytes >= ((size_t)B * cs * 8 + 512) * sizeof(long long)) {
-        PCL_CUDA(cudaLaunchKernelEx(&cfg, emd_auction_kernel<true>, p1, p2, N, eps, iters, flags, pcap, wpb_max, dist, (int *)assignment, (int *)stats, (long long *)workspace, (unsigned char *)nullptr));
+        PCL_CUDA(cudaLaunchKernelEx(&cfg, emd_auction_kernel<true>, p1, p2, N, eps, iters, flags, pcap, wpb_max, items_target, dist, (int *)assignment, (int *)stats, (long long *)workspace, (unsigned char *)nullptr));
     } else {
-        PCL_CUDA(cudaLaunchKernelEx(&cfg, emd_auction_kernel<false>, p1, p2, N, eps, iters, flags, pcap, wpb_max, dist, (int *)assignment, (int *)stats, (long long *)nullptr, (unsigned char *)((flags & EMD_F_COLD) ? workspace : nullptr)));
+        PCL_CUDA(cudaLaunchKernelEx(&cfg, emd_auction_kernel<false>, p1, p2, N, eps, iters, flags, pcap, wpb_max, items_target, dist, (int *)assignment, (int *)stats, (long long *)nullptr, (unsigned char *)((flags & EMD_F_COLD) ? workspace : nullptr)));
     }
     return PCL_OK;
 }
