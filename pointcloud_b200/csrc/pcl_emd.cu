@@ -45,7 +45,7 @@ namespace {
 constexpr int EMD_THREADS = 512;
 constexpr int EMD_WARPS = EMD_THREADS / 32;
 constexpr int EMD_MAX_N = 8192;      // 4097..8192: the cold half of the state lives in a per-CTA global-memory region (L2)
-constexpr int EMD_SMEM_ONLY_N = 4096;  // up to here the whole auction state fits into shared memory
+constexpr int EMD_SMEM_ONLY_N = 3584;  // up to here the whole auction state (58 B/point + 9 KB) fits into 227 KB of shared memory
 constexpr int TILE = 32;  // targets per spatial tile (one bounding box per tile)
 constexpr int EMD_WPB_MAX = 6 * EMD_WARPS;  // at most this many bidders per CTA: warp-per-bidder scan (swept on config 2: 48..128)
 constexpr unsigned short NONE16 = 0xffffu;
@@ -64,11 +64,12 @@ struct EmdSmem {
     float *maxinc;          // N   per-object running max increment (reference: max_increments)
     int *maxidx;            // N   per-object winning bidder, ORIGINAL index (reference: max_idx), -1 = none
     unsigned *last;         // N   previous bid of every bidder (object | second<<16), NOLAST = never bid
+    unsigned *last34;       // N   two more recent candidates of that bid (third | fourth<<16): extra seeds, never affect results
     unsigned short *asg;    // N8  assignment (pred -> target, internal indices), NONE16 = unassigned; padded with 0
     unsigned short *inv;    // N   assignment_inv (target -> pred), NONE16 = free
     unsigned short *unass;  // N   compacted list of unassigned bidders (internal pred indices, ascending)
     float *pbest, *pbetter; // pcap slice partials (pcap = 32 * max work items with a partial)
-    unsigned *pbi;          // pcap
+    unsigned *pbi, *pbi34;  // pcap
     int *wsum;              // 32
     unsigned long long *evals;  // 1   executed evaluations of the whole cluster (accumulated in rank 0's copy)
     float4 *tlo, *thi;      // NT  tile boxes: lo = {min xyz, max c of the tile}, hi = {max xyz, -}
@@ -77,14 +78,14 @@ struct EmdSmem {
     float4 *x1;             // N   predictions {x,y,z,0} in internal order (nullptr: read from global/L2)
 };
 
-// bytes of the "cold" arrays (touched O(U) times per iteration): pub 16, maxinc 4, maxidx 4, last 4, asg/inv/unass 6
+// bytes of the "cold" arrays (touched O(U) times per iteration): pub 16, maxinc 4, maxidx 4, last 4 + 4, asg/inv/unass 6
 __host__ __device__ inline size_t emd_cold_bytes(int N) {
     const size_t n8 = (size_t)(N + 7) / 8 * 8;
-    return n8 * (16 + 4 + 4 + 4) + n8 * 2 * 3;
+    return n8 * (16 + 4 + 4 + 4 + 4) + n8 * 2 * 3;
 }
 __host__ __device__ inline size_t emd_smem_bytes(int N, int flags, int pcap = EMD_THREADS) {
     const size_t n8 = (size_t)(N + 7) / 8 * 8, n32 = (size_t)(N + 31) / 32 * 32, nt = n32 / 32;
-    return n32 * 16 + n8 * 4 + ((flags & EMD_F_COLD) ? 0 : emd_cold_bytes(N)) + (size_t)pcap * 12 + 32 * 4 + 16 + nt * 32 +
+    return n32 * 16 + n8 * 4 + ((flags & EMD_F_COLD) ? 0 : emd_cold_bytes(N)) + (size_t)pcap * 16 + 32 * 4 + 16 + nt * 32 +
            ((flags & EMD_F_SORT) ? n8 * 4 : 0) + ((flags & EMD_F_X1) ? n8 * 16 : 0) + 64;
 }
 
@@ -102,6 +103,7 @@ __device__ inline EmdSmem carve(unsigned char *base, unsigned char *cold, int N,
     s.pbest = (float *)p; p += (size_t)pcap * 4;
     s.pbetter = (float *)p; p += (size_t)pcap * 4;
     s.pbi = (unsigned *)p; p += (size_t)pcap * 4;
+    s.pbi34 = (unsigned *)p; p += (size_t)pcap * 4;
     s.wsum = (int *)p; p += 32 * 4;
     s.evals = (unsigned long long *)p; p += 16;
     unsigned char *c = (flags & EMD_F_COLD) ? cold : p;  // same layout in shared memory or in the CTA's global region
@@ -112,6 +114,7 @@ __device__ inline EmdSmem carve(unsigned char *base, unsigned char *cold, int N,
     s.maxinc = (float *)c; c += n8 * 4;
     s.maxidx = (int *)c; c += n8 * 4;
     s.last = (unsigned *)c; c += n8 * 4;
+    s.last34 = (unsigned *)c; c += n8 * 4;
     return s;
 }
 
@@ -160,6 +163,7 @@ struct Top2 {
     float best, better;  // emd_cuda.cu:112
     int bi, bi2;         // internal index of the bid (first argmax in ORIGINAL index order) and of the runner-up
     int bio;             // original index of bi (tie rule: lowest original index among equal maxima)
+    int k3, k4;          // the two most recent "also-rans" (displaced runner-ups / survivors that missed the top two): seeds
     float tm;            // filter threshold: (lower bound of the final second best) - margin
 };
 
@@ -168,8 +172,9 @@ struct Top2 {
 __device__ __forceinline__ void top2_exact(const EmdSmem &S, Top2 &r, float s, int k) {
     const float v = bid_value_exact(s, S.pf[k]);
     const int ko = S.tperm ? (int)S.tperm[k] : k;
-    if (v > r.best || (v == r.best && ko < r.bio)) { r.better = r.best; r.bi2 = r.bi; r.best = v; r.bi = k; r.bio = ko; }
-    else if (v > r.better) { r.better = v; r.bi2 = k; }
+    if (v > r.best || (v == r.best && ko < r.bio)) { r.k4 = r.k3; r.k3 = r.bi2; r.better = r.best; r.bi2 = r.bi; r.best = v; r.bi = k; r.bio = ko; }
+    else if (v > r.better) { r.k4 = r.k3; r.k3 = r.bi2; r.better = v; r.bi2 = k; }
+    else { r.k4 = r.k3; r.k3 = k; }
     r.tm = fmaxf(r.tm, __fsub_rn(r.better, FILTER_MARGIN));
 }
 
@@ -209,17 +214,30 @@ __device__ __forceinline__ bool tile_skippable(const float4 &lo, const float4 &h
     return (u < 0.f) || (__fmaf_rn(u, u, -d2) < 0.f);
 }
 
-// Start of a scan: seed the threshold with the exact current values of the two objects this bidder
-// preferred last time (their prices may have risen since; any two distinct objects give a valid bound).
-__device__ __forceinline__ Top2 top2_init(const EmdSmem &S, unsigned lastpack, int N, float ax, float ay, float az) {
+// Start of a scan: seed the threshold with the exact CURRENT values of up to four objects this bidder met at its
+// previous bid (its top two and two also-rans; prices may have risen since).  The second largest of the values of
+// distinct objects is a valid lower bound of the final second best.
+__device__ __forceinline__ float seed_value(const EmdSmem &S, int k, float ax, float ay, float az) {
+    const float4 t = S.tgt[k];
+    return bid_value_exact(sq3_ref(__fsub_rn(t.x, ax), __fsub_rn(t.y, ay), __fsub_rn(t.z, az)), S.pf[k]);
+}
+__device__ __forceinline__ Top2 top2_init(const EmdSmem &S, unsigned lastpack, unsigned last34, int N, float ax, float ay, float az) {
     Top2 r;
-    r.best = -1e9f; r.better = -1e9f; r.bi = -1; r.bi2 = -1; r.bio = 0x7fffffff; r.tm = -1e9f;
+    r.best = -1e9f; r.better = -1e9f; r.bi = -1; r.bi2 = -1; r.bio = 0x7fffffff; r.k3 = -1; r.k4 = -1; r.tm = -1e9f;
     const int k1 = (int)(lastpack & 0xffffu), k2 = (int)(lastpack >> 16);
     if (lastpack != NOLAST && k1 < N && k2 < N && k1 != k2) {
-        const float4 t1 = S.tgt[k1], t2 = S.tgt[k2];
-        const float v1 = bid_value_exact(sq3_ref(__fsub_rn(t1.x, ax), __fsub_rn(t1.y, ay), __fsub_rn(t1.z, az)), S.pf[k1]);
-        const float v2 = bid_value_exact(sq3_ref(__fsub_rn(t2.x, ax), __fsub_rn(t2.y, ay), __fsub_rn(t2.z, az)), S.pf[k2]);
-        r.tm = __fsub_rn(fminf(v1, v2), FILTER_MARGIN);
+        float hi = seed_value(S, k1, ax, ay, az), lo = seed_value(S, k2, ax, ay, az);  // hi >= lo: the two largest so far
+        if (lo > hi) { const float t = hi; hi = lo; lo = t; }
+        const int k3 = (int)(last34 & 0xffffu), k4 = (int)(last34 >> 16);
+        if (k3 < N && k3 != k1 && k3 != k2) {
+            const float v = seed_value(S, k3, ax, ay, az);
+            if (v > hi) { lo = hi; hi = v; } else if (v > lo) lo = v;
+        }
+        if (k4 < N && k4 != k1 && k4 != k2 && k4 != k3) {
+            const float v = seed_value(S, k4, ax, ay, az);
+            if (v > hi) { lo = hi; hi = v; } else if (v > lo) lo = v;
+        }
+        r.tm = __fsub_rn(lo, FILTER_MARGIN);
     }
     return r;
 }
@@ -319,6 +337,7 @@ emd_auction_kernel(Pts xyz1, Pts xyz2, int N, float eps, int iters, int flags, i
         S.maxinc[j] = 0.f;
         S.maxidx[j] = -1;
         S.last[j] = NOLAST;
+        S.last34[j] = NOLAST;
     }
     __syncthreads();
     for (int t = wid; t < NT; t += EMD_WARPS) {  // tile boxes
@@ -425,15 +444,21 @@ emd_auction_kernel(Pts xyz1, Pts xyz2, int N, float eps, int iters, int flags, i
         const int GS = Gn * 32;                                          // partial stride of one slice
         uint2 *pub_cur = S.pub + cur * n8;
 
-        auto publish = [&](int jp, float best, float better, unsigned pack) {
+        auto publish = [&](int jp, float best, float better, unsigned pack, unsigned pack34) {
             const float inc = __fadd_rn(__fsub_rn(best, better), eps);  // emd_cuda.cu:175
             const uint2 v = make_uint2(pack, __float_as_uint(inc));
             if (flags & EMD_F_COLD) {  // peers' bid buffers are global-memory regions: plain stores, ordered by the cluster barrier
                 const size_t off = (size_t)(pub_cur - S.pub) + (size_t)jp;
-                for (int c = 0; c < cs; c++)
-                    reinterpret_cast<uint2 *>(cold_ws + ((size_t)cloud * cs + c) * cold_stride)[off] = v;
+                for (int c = 0; c < cs; c++) {
+                    unsigned char *peer = cold_ws + ((size_t)cloud * cs + c) * cold_stride;
+                    reinterpret_cast<uint2 *>(peer)[off] = v;
+                    reinterpret_cast<unsigned *>(peer + ((unsigned char *)S.last34 - (unsigned char *)S.pub))[jp] = pack34;
+                }
             } else {
-                for (int c = 0; c < cs; c++) cluster.map_shared_rank(pub_cur, c)[jp] = v;
+                for (int c = 0; c < cs; c++) {
+                    cluster.map_shared_rank(pub_cur, c)[jp] = v;
+                    cluster.map_shared_rank(S.last34, c)[jp] = pack34;  // read next in the bid phase after the coming barrier
+                }
             }
         };
 
@@ -448,22 +473,26 @@ emd_auction_kernel(Pts xyz1, Pts xyz2, int N, float eps, int iters, int flags, i
                 if (b >= Uc) break;
                 const int jp = S.unass[pos(b)];
                 const float3 a = pred_xyz(jp);
-                const unsigned lp = S.last[jp];
+                const unsigned lp = S.last[jp], lp34 = S.last34[jp];
                 float tm = -1e9f;
                 {
                     const int k1 = (int)(lp & 0xffffu), k2 = (int)(lp >> 16);
-                    if (lp != NOLAST && k1 < N && k2 < N && k1 != k2) {  // seeds: lanes 0 and 1 evaluate them in parallel
-                        float v = 0.f;
-                        if (lane < 2) {
-                            const int ks = lane ? k2 : k1;
-                            const float4 tq = S.tgt[ks];
-                            v = bid_value_exact(sq3_ref(__fsub_rn(tq.x, a.x), __fsub_rn(tq.y, a.y), __fsub_rn(tq.z, a.z)), S.pf[ks]);
-                        }
-                        tm = __fsub_rn(fminf(__shfl_sync(0xffffffffu, v, 0), __shfl_sync(0xffffffffu, v, 1)), FILTER_MARGIN);
+                    if (lp != NOLAST && k1 < N && k2 < N && k1 != k2) {  // seeds: lanes 0..3 evaluate up to four of them in parallel
+                        const int k3 = (int)(lp34 & 0xffffu), k4 = (int)(lp34 >> 16);
+                        const bool ok3 = k3 < N && k3 != k1 && k3 != k2, ok4 = k4 < N && k4 != k1 && k4 != k2 && k4 != k3;
+                        float v = -3e38f;
+                        const int ks = lane == 0 ? k1 : lane == 1 ? k2 : lane == 2 ? k3 : k4;
+                        if (lane < 2 || (lane == 2 && ok3) || (lane == 3 && ok4)) v = seed_value(S, ks, a.x, a.y, a.z);
+                        // second largest of the (up to) four values
+                        const float v0 = __shfl_sync(0xffffffffu, v, 0), v1 = __shfl_sync(0xffffffffu, v, 1),
+                                    v2 = __shfl_sync(0xffffffffu, v, 2), v3 = __shfl_sync(0xffffffffu, v, 3);
+                        const float hi01 = fmaxf(v0, v1), lo01 = fminf(v0, v1), hi23 = fmaxf(v2, v3), lo23 = fminf(v2, v3);
+                        const float second = fmaxf(fminf(hi01, hi23), fmaxf(lo01, lo23));
+                        tm = __fsub_rn(second, FILTER_MARGIN);
                     }
                 }
                 float best = -1e9f, better = -1e9f;
-                int bi = -1, bi2 = -1, bio = 0x7fffffff;
+                int bi = -1, bi2 = -1, bio = 0x7fffffff, k3 = -1, k4 = -1;
                 for (int tb = 0; tb < NT; tb += 32) {
                     const int tl = tb + lane;
                     bool cand = false;
@@ -512,14 +541,16 @@ emd_auction_kernel(Pts xyz1, Pts xyz2, int N, float eps, int iters, int flags, i
                                 pm &= pm - 1;
                                 const float vl = __shfl_sync(0xffffffffu, v, l);
                                 const int kol = __shfl_sync(0xffffffffu, ko, l), kl = __shfl_sync(0xffffffffu, ksel, l);
-                                if (vl > best || (vl == best && kol < bio)) { better = best; bi2 = bi; best = vl; bi = kl; bio = kol; }
-                                else if (vl > better) { better = vl; bi2 = kl; }
+                                if (vl > best || (vl == best && kol < bio)) { k4 = k3; k3 = bi2; better = best; bi2 = bi; best = vl; bi = kl; bio = kol; }
+                                else if (vl > better) { k4 = k3; k3 = bi2; better = vl; bi2 = kl; }
+                                else { k4 = k3; k3 = kl; }
                             }
                         } while (__any_sync(0xffffffffu, pass[0] || pass[1] || pass[2] || pass[3]));
                         tm = fmaxf(tm, __fsub_rn(better, FILTER_MARGIN));
                     }
                 }
-                if (lane == 0) publish(jp, best, better, (unsigned)(bi & 0xffff) | ((unsigned)(bi2 & 0xffff) << 16));
+                if (lane == 0) publish(jp, best, better, (unsigned)(bi & 0xffff) | ((unsigned)(bi2 & 0xffff) << 16),
+                                       (unsigned)(k3 & 0xffff) | ((unsigned)(k4 & 0xffff) << 16));
             }
         } else
         for (;;) {
@@ -532,7 +563,7 @@ emd_auction_kernel(Pts xyz1, Pts xyz2, int N, float eps, int iters, int flags, i
             const bool active = (g * 32 + lane) < Uc;
             const int jp = S.unass[pos(b)];
             const float3 a = pred_xyz(jp);
-            Top2 r = top2_init(S, S.last[jp], N, a.x, a.y, a.z);
+            Top2 r = top2_init(S, S.last[jp], S.last34[jp], N, a.x, a.y, a.z);
             const int ntl = (NT - sl + KS - 1) / KS;           // tiles of this slice: sl, sl+KS, ...
             const int home = min(max((__shfl_sync(0xffffffffu, jp, 0) / TILE - sl + KS / 2) / KS, 0), ntl - 1);
             for (int m = 0; m < ntl; m++) {                    // zig-zag outwards from the tile next to the bidders
@@ -545,10 +576,11 @@ emd_auction_kernel(Pts xyz1, Pts xyz2, int N, float eps, int iters, int flags, i
                 my_evals += active ? TILE : 0;
             }
             const unsigned pack = (unsigned)(r.bi & 0xffff) | ((unsigned)(r.bi2 & 0xffff) << 16);
+            const unsigned pack34 = (unsigned)(r.k3 & 0xffff) | ((unsigned)(r.k4 & 0xffff) << 16);
             if (KS == 1) {
-                if (active) publish(jp, r.best, r.better, pack);
+                if (active) publish(jp, r.best, r.better, pack, pack34);
             } else if (active) {
-                S.pbest[sl * GS + b] = r.best; S.pbetter[sl * GS + b] = r.better; S.pbi[sl * GS + b] = pack;
+                S.pbest[sl * GS + b] = r.best; S.pbetter[sl * GS + b] = r.better; S.pbi[sl * GS + b] = pack; S.pbi34[sl * GS + b] = pack34;
             }
         }
         if (!wpb && KS > 1) {
@@ -563,7 +595,7 @@ emd_auction_kernel(Pts xyz1, Pts xyz2, int N, float eps, int iters, int flags, i
                     const int c = idx / Uc, b = idx - c * Uc;
                     const int me = c * GS + b, ot = (c + st) * GS + b;
                     float best = S.pbest[me], better = S.pbetter[me];
-                    unsigned pk = S.pbi[me];
+                    unsigned pk = S.pbi[me], pk34 = S.pbi34[me];
                     const float ob = S.pbest[ot], obt = S.pbetter[ot];
                     const unsigned opk = S.pbi[ot];
                     bool other_wins = ob > best;
@@ -580,15 +612,16 @@ emd_auction_kernel(Pts xyz1, Pts xyz2, int N, float eps, int iters, int flags, i
                         better = fmaxf(best, obt);
                         best = ob;
                         pk = (opk & 0xffffu) | (second << 16);
+                        pk34 = S.pbi34[ot];  // also-rans of the slice that holds the best: spatially closest extra seeds
                     } else if (ob > better) {
                         better = ob;
                         pk = (pk & 0xffffu) | ((opk & 0xffffu) << 16);
                     }
-                    S.pbest[me] = best; S.pbetter[me] = better; S.pbi[me] = pk;
+                    S.pbest[me] = best; S.pbetter[me] = better; S.pbi[me] = pk; S.pbi34[me] = pk34;
                 }
                 __syncthreads();
             }
-            for (int b = tid; b < Uc; b += T) publish(S.unass[pos(b)], S.pbest[b], S.pbetter[b], S.pbi[b]);
+            for (int b = tid; b < Uc; b += T) publish(S.unass[pos(b)], S.pbest[b], S.pbetter[b], S.pbi[b], S.pbi34[b]);
         }
         if constexpr (PROF) {
             if (blockIdx.x == 0 && tid == 0 && prof && t < 50) {
