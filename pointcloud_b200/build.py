@@ -5,7 +5,7 @@ import sys
 
 HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
-LIB = os.path.join(HERE, "libpcl_b200.so")
+LIB = os.environ.get("PCL_LIB_OVERRIDE") or os.path.join(HERE, "libpcl_b200.so")  # override: development A/B builds
 SOURCES = ["pcl_api.cu", "pcl_chamfer.cu", "pcl_emd.cu", "pcl_sampling.cu"]
 HEADERS = [os.path.join(CSRC, "pcl_common.cuh"), os.path.join(HERE, "..", "include", "pcl.h")]
 NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17",
@@ -18,6 +18,8 @@ def _nvcc():
 
 
 def needs_build() -> bool:
+    if os.environ.get("PCL_LIB_OVERRIDE"):
+        return False
     if not os.path.exists(LIB):
         return True
     deps = [os.path.join(CSRC, s) for s in SOURCES] + HEADERS

@@ -37,7 +37,12 @@
 
 #include "pcl_common.cuh"
 
+#ifndef PCL_SCAN_UNROLL
+#define PCL_SCAN_UNROLL 4  // swept 1, 2, 4, 8 on config 2
+#endif
+
 namespace cg = cooperative_groups;
+constexpr int kScanUnroll = PCL_SCAN_UNROLL;  // groups of 4 targets per loop trip in the tile scan
 
 namespace pcl {
 namespace {
@@ -186,7 +191,7 @@ __device__ __forceinline__ void scan_tile(const EmdSmem &S, int k0, float ax, fl
     const float S_ = sq3_ref(__fsub_rn(T_.x, ax), __fsub_rn(T_.y, ay), __fsub_rn(T_.z, az));     \
     const float u_##E_ = __fsub_rn(T_.w, r.tm);                                                   \
     const float E_ = __fmaf_rn(u_##E_, u_##E_, -S_);
-#pragma unroll 2
+#pragma unroll kScanUnroll
     for (int k = k0; k < k0 + TILE; k += 4) {
         float e0, e1, e2, e3, s0, s1, s2, s3;
         { const int k_ = k;     PCL_FILTER(t, s, e) e0 = e; s0 = s; }
