@@ -37,6 +37,9 @@
 
 #include "pcl_common.cuh"
 
+#ifndef PCL_WPB_CHUNK
+#define PCL_WPB_CHUNK 4
+#endif
 #ifndef PCL_SCAN_UNROLL
 #define PCL_SCAN_UNROLL 4  // swept 1, 2, 4, 8 on config 2
 #endif
@@ -503,38 +506,42 @@ emd_auction_kernel(Pts xyz1, Pts xyz2, int N, float eps, int iters, int flags, i
                     bool cand = false;
                     if (tl < NT) cand = !tile_skippable(S.tlo[tl], S.thi[tl], a.x, a.y, a.z, tm);
                     unsigned cm = __ballot_sync(0xffffffffu, cand);
-                    while (cm) {  // up to 4 candidate tiles per step: 4 independent filter chains per lane, one vote
-                        int tix[4];
-                        bool have[4];
+                    constexpr int WC = PCL_WPB_CHUNK;
+                    while (cm) {  // up to WC candidate tiles per step: WC independent filter chains per lane, one vote
+                        int tix[WC];
+                        bool have[WC];
 #pragma unroll
-                        for (int i = 0; i < 4; i++) {
+                        for (int i = 0; i < WC; i++) {
                             have[i] = cm != 0;
                             tix[i] = tb + (have[i] ? __ffs(cm) - 1 : 0);
                             cm &= cm - 1;  // cm == 0 stays 0
                         }
-                        float sq[4];
-                        bool pass[4];
+                        float sq[WC];
+                        bool pass[WC];
                         bool any = false;
 #pragma unroll
-                        for (int i = 0; i < 4; i++) {
+                        for (int i = 0; i < WC; i++) {
                             const float4 tq = S.tgt[tix[i] * TILE + lane];
                             sq[i] = sq3_ref(__fsub_rn(tq.x, a.x), __fsub_rn(tq.y, a.y), __fsub_rn(tq.z, a.z));
                             const float u = __fsub_rn(tq.w, tm);
                             pass[i] = have[i] && !(__fmaf_rn(u, u, -sq[i]) < 0.f);
                             any |= pass[i];
                         }
-                        if (lane == 0) my_evals += TILE * ((int)have[0] + (int)have[1] + (int)have[2] + (int)have[3]);
+                        if (lane == 0) {
+#pragma unroll
+                            for (int i = 0; i < WC; i++) my_evals += have[i] ? TILE : 0;
+                        }
                         if (!__any_sync(0xffffffffu, any)) continue;
                         // Every lane takes ITS first surviving slot, so that one pass through the sqrt/F2F/DADD chain serves
                         // all lanes (a lane rarely has two survivors among its 4 targets; leftovers loop).
                         do {
                             int sel = -1;
 #pragma unroll
-                            for (int i = 3; i >= 0; i--) sel = pass[i] ? i : sel;
+                            for (int i = WC - 1; i >= 0; i--) sel = pass[i] ? i : sel;
                             float ssel = 0.f;
                             int ksel = 0;
 #pragma unroll
-                            for (int i = 0; i < 4; i++) {
+                            for (int i = 0; i < WC; i++) {
                                 if (sel == i) { ssel = sq[i]; ksel = tix[i] * TILE + lane; pass[i] = false; }
                             }
                             float v = 0.f;
@@ -550,7 +557,10 @@ emd_auction_kernel(Pts xyz1, Pts xyz2, int N, float eps, int iters, int flags, i
                                 else if (vl > better) { k4 = k3; k3 = bi2; better = vl; bi2 = kl; }
                                 else { k4 = k3; k3 = kl; }
                             }
-                        } while (__any_sync(0xffffffffu, pass[0] || pass[1] || pass[2] || pass[3]));
+                            any = false;
+#pragma unroll
+                            for (int i = 0; i < WC; i++) any |= pass[i];
+                        } while (__any_sync(0xffffffffu, any));
                         tm = fmaxf(tm, __fsub_rn(better, FILTER_MARGIN));
                     }
                 }
