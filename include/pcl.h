@@ -100,7 +100,7 @@ PCL_API int pcl_chamfer_bwd(const void *x, int x_dtype, int64_t x_bs, int64_t x_
  *          launch flags, tiles per cloud }.
  * Constraints: 1 <= N <= pcl_emd_max_points() (8192: the reference's own demo size, emd_module.py:82), B >= 0
  * (the reference needs N%1024==0 and B<=512, emd_cuda.cu:241-249; both are accepted here, neither is required).
- * Up to 4096 points the whole auction state lives in shared memory; above, half of it lives in `workspace`
+ * Up to 3584 points the whole auction state lives in shared memory; above, half of it lives in `workspace`
  * (>= pcl_emd_workspace_bytes(B, N), which then is tens of MB).
  * The GetMax race of the reference (emd_cuda.cu:188-191) is resolved deterministically: the
  * largest bidder index inside the +-1e-6 window wins.
