@@ -17,9 +17,40 @@
 namespace pcl {
 namespace {
 
-constexpr int CH_THREADS = 128;
-constexpr int CH_TILE = 1024;  // targets per shared-memory tile (16 KB)
-constexpr int CH_CHUNK = 32;   // argmin recovery granularity
+constexpr int CH_THREADS = 128;  // the generic-D kernel and the partial-sum layout: one slot per 128 queries
+#ifndef PCL_C3_QPT
+#define PCL_C3_QPT 2
+#endif
+#ifndef PCL_C3_WQ
+#define PCL_C3_WQ 4
+#endif
+#ifndef PCL_C3_PARTS
+#define PCL_C3_PARTS 1
+#endif
+constexpr int C3_QPT = PCL_C3_QPT;      // D == 3 kernel: register-resident queries per lane ...
+constexpr int C3_WQ = PCL_C3_WQ;        // ... warps with different queries ...
+constexpr int C3_PARTS = PCL_C3_PARTS;  // ... and warps that share the queries but scan different chunks of the targets (merged at the end)
+constexpr int C3_QUERIES = 32 * C3_QPT * C3_WQ;  // queries per CTA
+constexpr int C3_THREADS = 32 * C3_WQ * C3_PARTS;
+constexpr int C3_TILE = 1024;    // targets per shared-memory tile (16 KB), cut into ...
+constexpr int C3_CHUNK = 32;     // ... chunks of 32: the granularity of the approximate minimum and of the exact re-scan
+#ifndef PCL_C3_GROUP
+#define PCL_C3_GROUP 4
+#endif
+#ifndef PCL_C3_MINB
+#define PCL_C3_MINB 4
+#endif
+constexpr int C3_GROUP = PCL_C3_GROUP;      // pairs of targets per register buffer of the scan (double-buffered: hides the LDS latency)
+
+typedef unsigned long long u64;
+// sm_100a packed FP32: FFMA2 = two IEEE-rounded FMAs per instruction, same FLOP rate as FFMA at half the issue slots
+// (tools/microbench_packed.cu).  Only the approximate scan uses it: ptxas contracts mul.rn.f32x2 + add.rn.f32x2 into
+// FFMA2 (even with -fmad=false), so the oracle's unfused sums cannot be written with packed instructions.
+__device__ __forceinline__ u64 pk2(float lo, float hi) { u64 r; asm("mov.b64 %0, {%1, %2};" : "=l"(r) : "f"(lo), "f"(hi)); return r; }
+__device__ __forceinline__ float lo2(u64 v) { return __uint_as_float((unsigned)v); }
+__device__ __forceinline__ float hi2(u64 v) { return __uint_as_float((unsigned)(v >> 32)); }
+__device__ __forceinline__ u64 ffma2(u64 a, u64 b, u64 c) { u64 r; asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(r) : "l"(a), "l"(b), "l"(c)); return r; }
+__device__ __forceinline__ float fmin3(float a, float b, float c) { float r; asm("min.f32 %0, %1, %2, %3;" : "=f"(r) : "f"(a), "f"(b), "f"(c)); return r; }  // NaN operands are ignored
 
 template <bool FMA>
 __device__ __forceinline__ float sqdist3(float qx, float qy, float qz, const float4 &t) {
@@ -43,103 +74,207 @@ __device__ __forceinline__ float block_sum(float v, float *red /* >= NWARPS floa
     return s;  // valid on thread 0
 }
 
-// grid: (ceil(maxP / (128*QPT)), B, 2 directions); block: 128 query lanes x KSP target parts.
-// A CTA owns 128*QPT queries; its KSP groups of 4 warps scan interleaved 64-target chunks of every tile, so that
-// even the small (B=32, N=2048) problem keeps ~28 warps per SM busy while one broadcast LDS.128 still feeds QPT
-// evaluations.  Per evaluation only the running minimum is tracked (one FMNMX next to the 8 FMA-pipe operations);
-// the argmin is recovered per chunk, and parts are merged with an explicit lowest-index rule.
-template <bool FMA, int QPT, int KSP>
-__global__ void __launch_bounds__(CH_THREADS * KSP)
+__device__ __forceinline__ float finite_or_inf(float v) { return (v <= 3.0e38f) ? v : __int_as_float(0x7f800000); }  // NaN -> +inf
+
+// Exact re-scan of chunk c of the tile for one query.  Phase A evaluates the approximate distance once more (same
+// bound, same threshold thr = running minimum + E2) and collects the pairs of targets that pass it -- the exact nearest
+// neighbour always does; phase B gives those (one or two) the oracle's arithmetic and folds them into (best, bi) with the
+// explicit rule "smaller distance, then lower index", the order-independent form of knn's ascending strict-'<' scan.
+// Lanes re-scan DIFFERENT chunks; rotating the pair order by the lane id keeps the 8 lanes of an LDS.128 phase on 8
+// different bank groups.
+template <bool FMA>
+__device__ __forceinline__ void rescan_chunk(const float4 *tA, const float4 *tB, bool act, int c, int cnt, int t0, float qx,
+                                             float qy, float qz, u64 nqx, u64 nqy, u64 nqz, float thr, float &best, int &bi) {
+    unsigned pm = 0;
+    const int base = c * (C3_CHUNK / 2), rot = (int)threadIdx.x;
+#pragma unroll
+    for (int pp = 0; pp < C3_CHUNK / 2; pp++) {
+        const int o = (pp + rot) & (C3_CHUNK / 2 - 1);
+        const float4 a = tA[base + o], b = tB[base + o];
+        const u64 v = ffma2(pk2(b.x, b.y), nqz, ffma2(pk2(a.z, a.w), nqy, ffma2(pk2(a.x, a.y), nqx, pk2(b.z, b.w))));
+        pm |= (unsigned)(!(fminf(lo2(v), hi2(v)) > thr)) << o;
+    }
+    if (!act) pm = 0;
+    while (__any_sync(0xffffffffu, pm != 0)) {
+        if (pm) {
+            const int o = __ffs(pm) - 1;
+            pm &= pm - 1;
+            const float4 a = tA[base + o], b = tB[base + o];
+            const int j0 = 2 * (base + o), i0 = t0 + j0;
+            const float d0 = sqdist3<FMA>(qx, qy, qz, make_float4(a.x, a.z, b.x, 0.f));
+            const float d1 = sqdist3<FMA>(qx, qy, qz, make_float4(a.y, a.w, b.y, 0.f));
+            if (j0 < cnt && (d0 < best || (d0 == best && i0 < bi))) { best = d0; bi = i0; }
+            if (j0 + 1 < cnt && (d1 < best || (d1 == best && i0 + 1 < bi))) { best = d1; bi = i0 + 1; }
+        }
+    }
+}
+
+// Forward kernel for D == 3.  grid: (ceil(maxP / C3_QUERIES), B, 2 directions); block: WQ x PARTS warps, QPT queries per lane.
+//
+// The scan over the targets runs on an APPROXIMATE distance in expanded form,
+//     a(q,t) = |t|^2 - 2 q.t  =  fma(tz, -2qz, fma(ty, -2qy, fma(tx, -2qx, |t|^2)))      (= |q-t|^2 - |q|^2),
+// three FFMA2 per two targets instead of eight FP32 operations per target, and keeps only the minimum of a per
+// (query, 32-target chunk).  Results never depend on it: with u = 2^-24, |a + |q|^2 - d| <= u (21 |t|^2 + 15 |q|^2) for
+// the oracle's fp32 distance d (3 roundings in |t|^2, 3 in the FMAs on partial sums <= 2|t|^2 + |q|^2, <= 6 relative
+// roundings in d <= 2|q|^2 + 2|t|^2), so the chunk that holds the exact nearest neighbour k* satisfies, when it is
+// scanned and at any later time,
+//     chunk minimum <= (running minimum of a) + E2,   E2 = 2^-18 (max|t|^2 seen so far + |q|^2)   (> twice that bound).
+// Such a chunk is remembered per query when it is scanned (the most recent one in registers; when it is displaced and
+// still qualifies it moves into a bit mask), and before the tile leaves shared memory the remembered chunks (one,
+// rarely two) are re-scanned with the oracle's arithmetic (rescan_chunk), which alone decides
+// distance and index.  Non-finite or huge coordinates make E2 infinite, i.e. everything is re-scanned: slower, still exact.
+template <bool FMA>
+__global__ void __launch_bounds__(C3_THREADS, PCL_C3_MINB)
 chamfer_nn3_kernel(Pts x, const int64_t *__restrict__ x_len, Pts y, const int64_t *__restrict__ y_len, int P1, int P2,
                    float *__restrict__ dist_x, int *__restrict__ idx_x, float *__restrict__ dist_y,
                    int *__restrict__ idx_y, float *__restrict__ partial, int nblk) {
-    constexpr int NT = CH_THREADS * KSP;
-    __shared__ float4 tile[CH_TILE];
-    __shared__ float red[NT / 32];
-    static_assert(sizeof(float4) * CH_TILE >= (size_t)CH_THREADS * QPT * KSP * 8, "merge buffer aliases the tile");
-    const int dir = blockIdx.z, n = blockIdx.y;
+    __shared__ float4 tA[C3_TILE / 2 + C3_GROUP];  // per pair of targets {x0, x1, y0, y1} (+ slack for the read-ahead)
+    __shared__ float4 tB[C3_TILE / 2 + C3_GROUP];  //                     {z0, z1, |t0|^2, |t1|^2}
+    constexpr int C3_PPT = C3_TILE / C3_THREADS;   // staged points per thread and tile
+    constexpr int CP = C3_CHUNK / 2;               // pairs per chunk
+    __shared__ float red[C3_THREADS / 32];
+    __shared__ int tmax_bits;
+    const int dir = blockIdx.z, n = blockIdx.y, tid = threadIdx.x, lane = tid & 31, wq = (tid >> 5) % C3_WQ, part = (tid >> 5) / C3_WQ;
     const Pts q = dir ? y : x, t = dir ? x : y;
     const int PQ = dir ? P2 : P1;
-    const int q0 = blockIdx.x * (CH_THREADS * QPT);
+    const int q0 = blockIdx.x * C3_QUERIES;
     if (q0 >= PQ) return;  // block-uniform
     const int lq = dir ? (y_len ? (int)y_len[n] : P2) : (x_len ? (int)x_len[n] : P1);
     const int lt = dir ? (x_len ? (int)x_len[n] : P1) : (y_len ? (int)y_len[n] : P2);
     float *dist = (dir ? dist_y : dist_x) + (size_t)n * PQ;
     int *idx = (dir ? idx_y : idx_x) + (size_t)n * PQ;
-    const int ql = threadIdx.x & (CH_THREADS - 1), part = threadIdx.x / CH_THREADS;
+    const float INF = __int_as_float(0x7f800000);
 
-    float qx[QPT], qy[QPT], qz[QPT], best[QPT];
-    int bi[QPT], bchunk[QPT];
-    bool improved[QPT];
+    // query r of a lane: q0 + 32 (r WQ + wq) + lane; the PARTS warps with the same wq hold the same queries
+    float qx[C3_QPT], qy[C3_QPT], qz[C3_QPT], q2[C3_QPT], best[C3_QPT], mrun[C3_QPT];
+    u64 nqx[C3_QPT], nqy[C3_QPT], nqz[C3_QPT];
+    int bi[C3_QPT];
 #pragma unroll
-    for (int r = 0; r < QPT; r++) {
-        const int i = q0 + r * CH_THREADS + ql;
+    for (int r = 0; r < C3_QPT; r++) {
+        const int i = q0 + (r * C3_WQ + wq) * 32 + lane;
         float3 p = make_float3(0.f, 0.f, 0.f);
         if (i < lq) p = ld_xyz(q, n, i);
         qx[r] = p.x; qy[r] = p.y; qz[r] = p.z;
-        best[r] = __int_as_float(0x7f800000);  // +inf
-        bi[r] = 0x7fffffff; bchunk[r] = 0; improved[r] = false;
+        q2[r] = finite_or_inf(__fmaf_rn(p.z, p.z, __fmaf_rn(p.y, p.y, __fmul_rn(p.x, p.x))));
+        nqx[r] = pk2(-2.f * p.x, -2.f * p.x); nqy[r] = pk2(-2.f * p.y, -2.f * p.y); nqz[r] = pk2(-2.f * p.z, -2.f * p.z);
+        best[r] = INF; bi[r] = 0x7fffffff; mrun[r] = INF;
     }
-    if (q0 < lq) {  // block-uniform: blocks made only of padded rows skip the scan
-        for (int t0 = 0; t0 < lt; t0 += CH_TILE) {
-            const int cnt = min(CH_TILE, lt - t0);
-            for (int j = threadIdx.x; j < cnt; j += NT) {
-                const float3 p = ld_xyz(t, n, t0 + j);
-                tile[j] = make_float4(p.x, p.y, p.z, 0.f);
+    if (q0 < lq && lt > 0) {  // block-uniform: blocks made only of padded rows skip the scan
+        if (tid == 0) tmax_bits = 0;
+        float3 pre[C3_PPT];  // points of the next tile: loaded before the exact re-scans of the current one, stored after them
+        auto prefetch = [&](int t0) {
+#pragma unroll
+            for (int k = 0; k < C3_PPT; k++) {
+                const int j = t0 + k * C3_THREADS + tid;
+                pre[k] = (j < lt) ? ld_xyz(t, n, j) : make_float3(0.f, 0.f, 0.f);
+            }
+        };
+        prefetch(0);
+        __syncthreads();
+        for (int t0 = 0; t0 < lt; t0 += C3_TILE) {
+            const int cnt = min(C3_TILE, lt - t0);
+            const int nch = (cnt + C3_CHUNK - 1) / C3_CHUNK;
+            {   // registers -> shared memory (pair layout), |t|^2, running maximum of |t|^2; padding: a = +inf, never a minimum
+                float wmax = 0.f;
+                float *fA = reinterpret_cast<float *>(tA), *fB = reinterpret_cast<float *>(tB);
+#pragma unroll
+                for (int k = 0; k < C3_PPT; k++) {
+                    const int j = k * C3_THREADS + tid;
+                    const float3 p = pre[k];
+                    float w = __fmaf_rn(p.z, p.z, __fmaf_rn(p.y, p.y, __fmul_rn(p.x, p.x)));
+                    if (j < cnt) wmax = fmaxf(wmax, finite_or_inf(w)); else w = INF;
+                    const int o = (j >> 1) * 4 + (j & 1);
+                    fA[o] = p.x; fA[o + 2] = p.y; fB[o] = p.z; fB[o + 2] = w;
+                }
+                const int wm = __reduce_max_sync(0xffffffffu, __float_as_int(wmax));  // wmax >= 0: integer order == float order
+                if (lane == 0) atomicMax(&tmax_bits, wm);
             }
             __syncthreads();
-            // strict '<' between this part's chunks (ascending) keeps its earliest chunk; the re-scan below returns the
-            // lowest index inside it -- together with the index-aware merge: "lowest index wins ties", as in knn's scan.
-            for (int c0 = part * CH_CHUNK; c0 < cnt; c0 += CH_CHUNK * KSP) {
-                const int c1 = min(c0 + CH_CHUNK, cnt);
-                float mc[QPT];
+            const float tmax = __int_as_float(tmax_bits);
+            float e2[C3_QPT], thr[C3_QPT], lm[C3_QPT];
+            int lcid[C3_QPT];       // chunk of the most recent candidate (lm = its approximate minimum)
+            unsigned dmask[C3_QPT]; // displaced candidates that still qualified when they were displaced
 #pragma unroll
-                for (int r = 0; r < QPT; r++) mc[r] = __int_as_float(0x7f800000);
-#pragma unroll 8
-                for (int j = c0; j < c1; j++) {
-                    const float4 tp = tile[j];
+            for (int r = 0; r < C3_QPT; r++) {
+                e2[r] = fmaxf(__fmul_ru(__fadd_ru(tmax, q2[r]), 3.8147e-6f /* > 2^-18 */), 1e-36f);
+                thr[r] = __fadd_ru(mrun[r], e2[r]);
+                lm[r] = INF; lcid[r] = 0; dmask[r] = 0;
+            }
+            float4 ga[C3_GROUP], gb[C3_GROUP];  // current group of pairs; the next one is loaded while this one is used
 #pragma unroll
-                    for (int r = 0; r < QPT; r++) mc[r] = fminf(mc[r], sqdist3<FMA>(qx[r], qy[r], qz[r], tp));
+            for (int i = 0; i < C3_GROUP; i++) { ga[i] = tA[part * CP + i]; gb[i] = tB[part * CP + i]; }
+            for (int c = part; c < nch; c += C3_PARTS) {
+                float mc[C3_QPT];
+#pragma unroll
+                for (int r = 0; r < C3_QPT; r++) mc[r] = INF;
+#pragma unroll
+                for (int g = 0; g < CP / C3_GROUP; g++) {
+                    float4 na[C3_GROUP], nb[C3_GROUP];
+                    // next group of this chunk, or the first group of this warp's next chunk (clamped into the slack at the end)
+                    const int nxt = min((g + 1 < CP / C3_GROUP) ? c * CP + (g + 1) * C3_GROUP : (c + C3_PARTS) * CP, C3_TILE / 2);
+#pragma unroll
+                    for (int i = 0; i < C3_GROUP; i++) { na[i] = tA[nxt + i]; nb[i] = tB[nxt + i]; }
+#pragma unroll
+                    for (int i = 0; i < C3_GROUP; i++) {
+                        const u64 tx = pk2(ga[i].x, ga[i].y), ty = pk2(ga[i].z, ga[i].w), tz = pk2(gb[i].x, gb[i].y), tw = pk2(gb[i].z, gb[i].w);
+#pragma unroll
+                        for (int r = 0; r < C3_QPT; r++) {
+                            const u64 v = ffma2(tz, nqz[r], ffma2(ty, nqy[r], ffma2(tx, nqx[r], tw)));
+                            mc[r] = fmin3(mc[r], lo2(v), hi2(v));
+                        }
+                    }
+#pragma unroll
+                    for (int i = 0; i < C3_GROUP; i++) { ga[i] = na[i]; gb[i] = nb[i]; }
                 }
 #pragma unroll
-                for (int r = 0; r < QPT; r++)
-                    if (mc[r] < best[r]) { best[r] = mc[r]; bchunk[r] = c0; improved[r] = true; }
+                for (int r = 0; r < C3_QPT; r++) {  // branch-free: a chunk that may hold the exact nearest neighbour becomes the candidate
+                    const bool cand = !(mc[r] > thr[r]);
+                    const float nm = fminf(mrun[r], mc[r]);     // == mrun unless cand
+                    const float nthr = __fadd_ru(nm, e2[r]);
+                    const bool keep = cand && !(lm[r] > nthr);  // the displaced candidate still qualifies (lm = +inf: none yet)
+                    dmask[r] |= keep ? (1u << lcid[r]) : 0u;
+                    lm[r] = cand ? mc[r] : lm[r];
+                    lcid[r] = cand ? c : lcid[r];
+                    mrun[r] = nm; thr[r] = nthr;
+                }
             }
+            if (t0 + C3_TILE < lt) prefetch(t0 + C3_TILE);
+            // exact re-scan of the remembered chunks while the tile is resident
 #pragma unroll
-            for (int r = 0; r < QPT; r++) {
-                if (improved[r]) {  // the tile is still in shared memory: find the lowest index that attains the minimum
-                    // Every lane re-scans a DIFFERENT chunk; chunks are 1 KB apart, i.e. the same banks.  Rotating the
-                    // start by the lane id makes the 32 LDS.128 of a step hit 32 consecutive float4 (conflict-free).
-                    const int c0 = bchunk[r], c1 = min(c0 + CH_CHUNK, cnt);
-                    int found = 0x7fffffff;
-#pragma unroll 4
-                    for (int jj = 0; jj < CH_CHUNK; jj++) {
-                        const int j = c0 + ((jj + (int)threadIdx.x) & (CH_CHUNK - 1));
-                        if (j < c1 && sqdist3<FMA>(qx[r], qy[r], qz[r], tile[j]) == best[r]) found = min(found, j);
-                    }
-                    bi[r] = t0 + found;
-                    improved[r] = false;
+            for (int r = 0; r < C3_QPT; r++) {
+                unsigned m = dmask[r];
+                if (!(lm[r] > thr[r])) m |= 1u << lcid[r];
+                if (q0 + (r * C3_WQ + wq) * 32 + lane >= lq) m = 0;
+                while (__any_sync(0xffffffffu, m != 0)) {
+                    const bool act = m != 0;
+                    const int c = act ? (__ffs(m) - 1) : 0;
+                    m &= m - 1;
+                    rescan_chunk<FMA>(tA, tB, act, c, cnt, t0, qx[r], qy[r], qz[r], nqx[r], nqy[r], nqz[r], thr[r], best[r], bi[r]);
                 }
             }
             __syncthreads();
         }
     }
-    if constexpr (KSP > 1) {  // merge the parts: minimum distance, lowest index among equal minima
-        float *mb = reinterpret_cast<float *>(tile);
-        int *mi = reinterpret_cast<int *>(tile) + CH_THREADS * QPT * KSP;
+    // merge the parts (smaller distance, then lower index) -- the tile buffers are free now
+    if constexpr (C3_PARTS > 1) {
+        static_assert((C3_PARTS - 1) * C3_QUERIES * 4 <= (int)sizeof(float4) * (C3_TILE / 2), "merge buffer fits into a tile array");
+        float *mb = reinterpret_cast<float *>(tA);
+        int *mi = reinterpret_cast<int *>(tB);
+        if (part > 0) {
 #pragma unroll
-        for (int r = 0; r < QPT; r++) {
-            mb[(part * QPT + r) * CH_THREADS + ql] = best[r];
-            mi[(part * QPT + r) * CH_THREADS + ql] = bi[r];
+            for (int r = 0; r < C3_QPT; r++) {
+                mb[(part - 1) * C3_QUERIES + (r * C3_WQ + wq) * 32 + lane] = best[r];
+                mi[(part - 1) * C3_QUERIES + (r * C3_WQ + wq) * 32 + lane] = bi[r];
+            }
         }
         __syncthreads();
         if (part == 0) {
 #pragma unroll
-            for (int r = 0; r < QPT; r++) {
+            for (int r = 0; r < C3_QPT; r++) {
 #pragma unroll
-                for (int pp = 1; pp < KSP; pp++) {
-                    const float ob = mb[(pp * QPT + r) * CH_THREADS + ql];
-                    const int oi = mi[(pp * QPT + r) * CH_THREADS + ql];
+                for (int pp = 1; pp < C3_PARTS; pp++) {
+                    const float ob = mb[(pp - 1) * C3_QUERIES + (r * C3_WQ + wq) * 32 + lane];
+                    const int oi = mi[(pp - 1) * C3_QUERIES + (r * C3_WQ + wq) * 32 + lane];
                     if (ob < best[r] || (ob == best[r] && oi < bi[r])) { best[r] = ob; bi[r] = oi; }
                 }
             }
@@ -148,17 +283,17 @@ chamfer_nn3_kernel(Pts x, const int64_t *__restrict__ x_len, Pts y, const int64_
     float s = 0.f;
     if (part == 0) {
 #pragma unroll
-        for (int r = 0; r < QPT; r++) {
-            const int i = q0 + r * CH_THREADS + ql;
+        for (int r = 0; r < C3_QPT; r++) {
+            const int i = q0 + (r * C3_WQ + wq) * 32 + lane;
             if (i < PQ) {
                 const bool valid = (i < lq) && (lt > 0);
                 const float d = valid ? best[r] : 0.f;
-                dist[i] = d; idx[i] = (valid && bi[r] != 0x7fffffff) ? bi[r] : 0;
+                dist[i] = d; idx[i] = (valid && bi[r] != 0x7fffffff && best[r] < INF) ? bi[r] : 0;  // no finite distance: knn's initial index 0
                 s += d;
             }
         }
     }
-    s = block_sum<NT / 32>(s, red);
+    s = block_sum<C3_THREADS / 32>(s, red);
     if (threadIdx.x == 0) partial[((size_t)dir * gridDim.y + n) * nblk + blockIdx.x] = s;
 }
 
@@ -273,26 +408,9 @@ int launch_fwd(const Pts &x, const int64_t *x_len, const Pts &y, const int64_t *
                cudaStream_t st) {
     const int maxP = P1 > P2 ? P1 : P2;
     if (D == 3) {
-        // 128*QPT queries per CTA; KSP target parts per CTA keep the warp count per SM high on small problems
-        const long queries = (long)B * ((long)P1 + P2);
-        int qpt = 4;
-        while (qpt > 1 && queries / (CH_THREADS * qpt) < 6L * sm_count) qpt >>= 1;
-        int ksp = 1;  // target-part split: measured slower on B200 at every size tried (profiles/r1_chamfer_variants.txt); kept as an option
-        if (const char *e = getenv("PCL_CHAMFER_QPT")) { const int v = atoi(e); if (v == 1 || v == 2 || v == 4) qpt = v; }  // development aid
-        if (const char *e = getenv("PCL_CHAMFER_KSP")) { const int v = atoi(e); if (v == 1 || v == 4) ksp = v; }
-        dim3 grid((maxP + CH_THREADS * qpt - 1) / (CH_THREADS * qpt), B, 2);
-#define PCL_LAUNCH_NN3(Q, K) \
-    chamfer_nn3_kernel<FMA, Q, K><<<grid, CH_THREADS * K, 0, st>>>(x, x_len, y, y_len, P1, P2, dist_x, idx_x, dist_y, idx_y, partial, nblk)
-        if (ksp == 4) {
-            if (qpt == 4) PCL_LAUNCH_NN3(4, 4);
-            else if (qpt == 2) PCL_LAUNCH_NN3(2, 4);
-            else PCL_LAUNCH_NN3(1, 4);
-        } else {
-            if (qpt == 4) PCL_LAUNCH_NN3(4, 1);
-            else if (qpt == 2) PCL_LAUNCH_NN3(2, 1);
-            else PCL_LAUNCH_NN3(1, 1);
-        }
-#undef PCL_LAUNCH_NN3
+        dim3 grid((maxP + C3_QUERIES - 1) / C3_QUERIES, B, 2);
+        chamfer_nn3_kernel<FMA><<<grid, C3_THREADS, 0, st>>>(x, x_len, y, y_len, P1, P2, dist_x, idx_x, dist_y, idx_y, partial, nblk);
+        (void)sm_count;
     } else {
         dim3 grid((maxP + CH_THREADS - 1) / CH_THREADS, B, 2);
 #define PCL_LAUNCH_NND(DD) \
@@ -318,7 +436,8 @@ int check_args(const void *x, int x_dtype, const void *y, int y_dtype, int B, in
 
 inline int nblk_for(int P1, int P2) {
     const int maxP = P1 > P2 ? P1 : P2;
-    return (maxP + CH_THREADS - 1) / CH_THREADS + 1;  // upper bound for every QPT
+    constexpr int G = C3_QUERIES < CH_THREADS ? C3_QUERIES : CH_THREADS;  // queries per CTA of the finer-grained kernel
+    return (maxP + G - 1) / G + 1;
 }
 
 }  // namespace

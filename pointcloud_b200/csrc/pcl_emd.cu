@@ -50,7 +50,10 @@ constexpr int kScanUnroll = PCL_SCAN_UNROLL;  // groups of 4 targets per loop tr
 namespace pcl {
 namespace {
 
-constexpr int EMD_THREADS = 512;
+#ifndef PCL_EMD_THREADS
+#define PCL_EMD_THREADS 512
+#endif
+constexpr int EMD_THREADS = PCL_EMD_THREADS;
 constexpr int EMD_WARPS = EMD_THREADS / 32;
 constexpr int EMD_MAX_N = 8192;      // 4097..8192: the cold half of the state lives in a per-CTA global-memory region (L2)
 constexpr int EMD_SMEM_ONLY_N = 3584;  // up to here the whole auction state (58 B/point + 9 KB) fits into 227 KB of shared memory
@@ -78,7 +81,7 @@ struct EmdSmem {
     unsigned short *unass;  // N   compacted list of unassigned bidders (internal pred indices, ascending)
     float *pbest, *pbetter; // pcap slice partials (pcap = 32 * max work items with a partial)
     unsigned *pbi, *pbi34;  // pcap
-    int *wsum;              // 32
+    int *wsum;              // 64: [0..31] warp sums, [48] work counter
     unsigned long long *evals;  // 1   executed evaluations of the whole cluster (accumulated in rank 0's copy)
     float4 *tlo, *thi;      // NT  tile boxes: lo = {min xyz, max c of the tile}, hi = {max xyz, -}
     unsigned short *tperm;  // N   internal target index -> original index (nullptr: identity)
@@ -93,7 +96,7 @@ __host__ __device__ inline size_t emd_cold_bytes(int N) {
 }
 __host__ __device__ inline size_t emd_smem_bytes(int N, int flags, int pcap = EMD_THREADS) {
     const size_t n8 = (size_t)(N + 7) / 8 * 8, n32 = (size_t)(N + 31) / 32 * 32, nt = n32 / 32;
-    return n32 * 16 + n8 * 4 + ((flags & EMD_F_COLD) ? 0 : emd_cold_bytes(N)) + (size_t)pcap * 16 + 32 * 4 + 16 + nt * 32 +
+    return n32 * 16 + n8 * 4 + ((flags & EMD_F_COLD) ? 0 : emd_cold_bytes(N)) + (size_t)pcap * 16 + 64 * 4 + 16 + nt * 32 +
            ((flags & EMD_F_SORT) ? n8 * 4 : 0) + ((flags & EMD_F_X1) ? n8 * 16 : 0) + 64;
 }
 
@@ -112,7 +115,7 @@ __device__ inline EmdSmem carve(unsigned char *base, unsigned char *cold, int N,
     s.pbetter = (float *)p; p += (size_t)pcap * 4;
     s.pbi = (unsigned *)p; p += (size_t)pcap * 4;
     s.pbi34 = (unsigned *)p; p += (size_t)pcap * 4;
-    s.wsum = (int *)p; p += 32 * 4;
+    s.wsum = (int *)p; p += 64 * 4;
     s.evals = (unsigned long long *)p; p += 16;
     unsigned char *c = (flags & EMD_F_COLD) ? cold : p;  // same layout in shared memory or in the CTA's global region
     s.pub = (uint2 *)c; c += n8 * 16;
@@ -273,7 +276,7 @@ emd_auction_kernel(Pts xyz1, Pts xyz2, int N, float eps, int iters, int flags, i
     const int tid = threadIdx.x, T = EMD_THREADS, lane = tid & 31, wid = tid >> 5;
     const size_t cold_stride = (emd_cold_bytes(N) + 255) / 256 * 256;
     const EmdSmem S = carve(smem_raw, (flags & EMD_F_COLD) ? cold_ws + (size_t)blockIdx.x * cold_stride : nullptr, N, flags, pcap);
-    int *const work_ctr = S.wsum + 24;  // dynamic work-item counter of the bid phase (wsum[0..15] = warp sums)
+    int *const work_ctr = S.wsum + 48;  // dynamic work-item counter of the bid phase (wsum[0..31] = warp sums)
     const int n8 = (N + 7) / 8 * 8, n32 = (N + 31) / 32 * 32, NT = n32 / TILE;
 
     // ---- init: internal (Morton) order of both clouds, tiles, auction state (emd_module.py:45-56) ----------

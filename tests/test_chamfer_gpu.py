@@ -47,6 +47,29 @@ def test_chamfer_table_shaped_and_ties():
     run_case(xg, yg)
 
 
+def test_chamfer_filter_stress():
+    """The kernel scans an approximate expanded-form distance and re-scans candidate chunks exactly; these inputs
+    make the approximation useless (far from the origin, huge / mixed scales, all points equal) or non-finite."""
+    g = torch.Generator().manual_seed(13)
+    x, y = torch.rand(2, 700, 3, generator=g), torch.rand(2, 1100, 3, generator=g)
+    for off in (10.0, 1000.0, -3.0e4):          # |t|^2 >> nearest-neighbour distances: every chunk is a candidate
+        run_case(x + off, y + off)
+        run_case(x * 0.01 + off, y * 0.01 + off, mode="fma")
+    run_case(x * 1e-3, y * 1e-3)
+    run_case(x * 1e-18, y * 1e-18)                # squared distances underflow towards denormals
+    run_case(x * 1e15, y * 1e15)                  # |t|^2 = 1e30: large but finite
+    run_case(x * 1e19, y * 1e19)                  # |t|^2 overflows to +inf while the exact distances stay finite
+    scale = torch.logspace(-6, 6, 1100).view(1, -1, 1)
+    run_case(x, y * scale)                        # one cloud mixes 12 orders of magnitude
+    run_case(torch.full((2, 300, 3), 0.25), torch.full((2, 2000, 3), 0.25))  # all equal: index 0 everywhere
+    z = y.clone(); z[:, 5::7] = z[:, 4::7][:, : z[:, 5::7].shape[1]]          # many exact duplicates
+    run_case(x, z)
+    yn = y.clone(); yn[0, 17, 1] = float("nan"); yn[1, 3, 0] = float("inf"); yn[1, 600, 2] = -float("inf")
+    o = oracle.chamfer_forward(x, yn, mode=0)
+    r = pcl.chamfer_forward_raw(x.cuda(), yn.cuda())
+    assert np.array_equal(npy(r["idx_x"]), o["idx_x"]) and np.array_equal(npy(r["dist_x"]), o["dist_x"])   # non-finite targets are never nearest
+
+
 def test_chamfer_variable_lengths_and_empty():
     g = torch.Generator().manual_seed(7)
     x, y = torch.rand(4, 820, 3, generator=g), torch.rand(4, 1500, 3, generator=g)
