@@ -232,9 +232,18 @@ __device__ __forceinline__ float seed_value(const EmdSmem &S, int k, float ax, f
     const float4 t = S.tgt[k];
     return bid_value_exact(sq3_ref(__fsub_rn(t.x, ax), __fsub_rn(t.y, ay), __fsub_rn(t.z, az)), S.pf[k]);
 }
-__device__ __forceinline__ Top2 top2_init(const EmdSmem &S, unsigned lastpack, unsigned last34, int N, float ax, float ay, float az) {
-    Top2 r;
-    r.best = -1e9f; r.better = -1e9f; r.bi = -1; r.bi2 = -1; r.bio = 0x7fffffff; r.k3 = -1; r.k4 = -1; r.tm = -1e9f;
+// Seeds of a bidder that has not bid yet (the first iteration): both clouds are in Morton order, so the targets of
+// similar rank are spatial neighbours.  Like all seeds they only tighten the filter threshold, never a result.
+__device__ __forceinline__ void first_seeds(int jp, int N, unsigned &lastpack, unsigned &last34) {
+    if (lastpack != NOLAST || N < 4) return;
+    const int k1 = min(max(jp, 1), N - 3);
+    lastpack = (unsigned)k1 | ((unsigned)(k1 - 1) << 16);
+    last34 = (unsigned)(k1 + 1) | ((unsigned)(k1 + 2) << 16);
+}
+
+// Filter threshold from the seeds: (second largest of the exact current values of up to four distinct objects) - margin
+__device__ __forceinline__ float seed_threshold(const EmdSmem &S, unsigned lastpack, unsigned last34, int N, float ax, float ay, float az) {
+    float tm = -1e9f;
     const int k1 = (int)(lastpack & 0xffffu), k2 = (int)(lastpack >> 16);
     if (lastpack != NOLAST && k1 < N && k2 < N && k1 != k2) {
         float hi = seed_value(S, k1, ax, ay, az), lo = seed_value(S, k2, ax, ay, az);  // hi >= lo: the two largest so far
@@ -248,8 +257,13 @@ __device__ __forceinline__ Top2 top2_init(const EmdSmem &S, unsigned lastpack, u
             const float v = seed_value(S, k4, ax, ay, az);
             if (v > hi) { lo = hi; hi = v; } else if (v > lo) lo = v;
         }
-        r.tm = __fsub_rn(lo, FILTER_MARGIN);
+        tm = __fsub_rn(lo, FILTER_MARGIN);
     }
+    return tm;
+}
+__device__ __forceinline__ Top2 top2_init(float tm) {
+    Top2 r;
+    r.best = -1e9f; r.better = -1e9f; r.bi = -1; r.bi2 = -1; r.bio = 0x7fffffff; r.k3 = -1; r.k4 = -1; r.tm = tm;
     return r;
 }
 
@@ -261,7 +275,7 @@ emd_auction_kernel(Pts xyz1, Pts xyz2, int N, float eps, int iters, int flags, i
                    float *__restrict__ dist,
                    int *__restrict__ assignment, int *__restrict__ stats, long long *__restrict__ prof,
                    unsigned char *__restrict__ cold_ws) {
-    long long pt[8] = {0, 0, 0, 0, 0, 0, 0, 0}, pc = 0;
+    long long pt[16] = {0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0}, pc = 0, bid0 = 0;
 #define PCL_TICK(i)                                              \
     if constexpr (PROF) {                                        \
         const long long now_ = clock64();                        \
@@ -434,6 +448,7 @@ emd_auction_kernel(Pts xyz1, Pts xyz2, int N, float eps, int iters, int flags, i
         sum_u += U;
         iters_run = t + 1;
         PCL_TICK(1)
+        if constexpr (PROF) bid0 = pc;
 
         // ---- 2. Bid (emd_cuda.cu:95-179) for this CTA's share of the bidders ----------------------------
         // A warp owns 32 consecutive (= spatially close) bidders and one interleaved slice of the target tiles;
@@ -484,7 +499,8 @@ emd_auction_kernel(Pts xyz1, Pts xyz2, int N, float eps, int iters, int flags, i
                 if (b >= Uc) break;
                 const int jp = S.unass[pos(b)];
                 const float3 a = pred_xyz(jp);
-                const unsigned lp = S.last[jp], lp34 = S.last34[jp];
+                unsigned lp = S.last[jp], lp34 = S.last34[jp];
+                if (flags & EMD_F_SORT) first_seeds(jp, N, lp, lp34);
                 float tm = -1e9f;
                 {
                     const int k1 = (int)(lp & 0xffffu), k2 = (int)(lp >> 16);
@@ -570,7 +586,19 @@ emd_auction_kernel(Pts xyz1, Pts xyz2, int N, float eps, int iters, int flags, i
                 if (lane == 0) publish(jp, best, better, (unsigned)(bi & 0xffff) | ((unsigned)(bi2 & 0xffff) << 16),
                                        (unsigned)(k3 & 0xffff) | ((unsigned)(k4 & 0xffff) << 16));
             }
-        } else
+            PCL_TICK(8)
+        } else {
+        // seed thresholds once per bidder (not once per slice item): parked in the increment field of the bidder's own
+        // bid slot, which nobody else touches before this CTA publishes that bid
+        for (int b = tid; b < Uc; b += T) {
+            const int jp = S.unass[pos(b)];
+            const float3 a = pred_xyz(jp);
+            unsigned lp = S.last[jp], lp34 = S.last34[jp];
+            if (flags & EMD_F_SORT) first_seeds(jp, N, lp, lp34);
+            pub_cur[jp].y = __float_as_uint(seed_threshold(S, lp, lp34, N, a.x, a.y, a.z));
+        }
+        __syncthreads();
+        PCL_TICK(6)
         for (;;) {
             int it = 0;
             if (lane == 0) it = atomicAdd(work_ctr, 1);
@@ -581,7 +609,7 @@ emd_auction_kernel(Pts xyz1, Pts xyz2, int N, float eps, int iters, int flags, i
             const bool active = (g * 32 + lane) < Uc;
             const int jp = S.unass[pos(b)];
             const float3 a = pred_xyz(jp);
-            Top2 r = top2_init(S, S.last[jp], S.last34[jp], N, a.x, a.y, a.z);
+            Top2 r = top2_init(__uint_as_float(pub_cur[jp].y));
             const int ntl = (NT - sl + KS - 1) / KS;           // tiles of this slice: sl, sl+KS, ...
             const int home = min(max((__shfl_sync(0xffffffffu, jp, 0) / TILE - sl + KS / 2) / KS, 0), ntl - 1);
             for (int m = 0; m < ntl; m++) {                    // zig-zag outwards from the tile next to the bidders
@@ -600,6 +628,8 @@ emd_auction_kernel(Pts xyz1, Pts xyz2, int N, float eps, int iters, int flags, i
             } else if (active) {
                 S.pbest[sl * GS + b] = r.best; S.pbetter[sl * GS + b] = r.better; S.pbi[sl * GS + b] = pack; S.pbi34[sl * GS + b] = pack34;
             }
+        }
+        PCL_TICK(2)
         }
         if (!wpb && KS > 1) {
             __syncthreads();
@@ -639,19 +669,20 @@ emd_auction_kernel(Pts xyz1, Pts xyz2, int N, float eps, int iters, int flags, i
                 }
                 __syncthreads();
             }
+            PCL_TICK(9)
             for (int b = tid; b < Uc; b += T) publish(S.unass[pos(b)], S.pbest[b], S.pbetter[b], S.pbi[b], S.pbi34[b]);
         }
         if constexpr (PROF) {
             if (blockIdx.x == 0 && tid == 0 && prof && t < 50) {
-                prof[(size_t)gridDim.x * 8 + t * 4] = U;
-                prof[(size_t)gridDim.x * 8 + t * 4 + 1] = clock64() - pc;
-                prof[(size_t)gridDim.x * 8 + t * 4 + 2] = KS * 1000 + Gn;
+                prof[(size_t)gridDim.x * 16 + t * 4] = U;
+                prof[(size_t)gridDim.x * 16 + t * 4 + 1] = clock64() - bid0;
+                prof[(size_t)gridDim.x * 16 + t * 4 + 2] = KS * 1000 + Gn;
             }
         }
-        PCL_TICK(2)
+        PCL_TICK(7)
         cluster.sync();  // all bids of this iteration are visible in every CTA
         if constexpr (PROF) {
-            if (blockIdx.x == 0 && tid == 0 && prof && t < 50) prof[(size_t)gridDim.x * 8 + t * 4 + 3] = clock64() - pc;
+            if (blockIdx.x == 0 && tid == 0 && prof && t < 50) prof[(size_t)gridDim.x * 16 + t * 4 + 3] = clock64() - pc;
         }
         PCL_TICK(3)
 
@@ -723,7 +754,7 @@ emd_auction_kernel(Pts xyz1, Pts xyz2, int N, float eps, int iters, int flags, i
     PCL_TICK(5)
     if constexpr (PROF) {
         if (tid == 0 && prof)
-            for (int i = 0; i < 8; i++) prof[(size_t)blockIdx.x * 8 + i] = pt[i];
+            for (int i = 0; i < 16; i++) prof[(size_t)blockIdx.x * 16 + i] = pt[i];
     }
 #undef PCL_TICK
     if (stats) {  // uniform over the grid
@@ -874,7 +905,7 @@ extern "C" int pcl_emd_max_points(void) { return EMD_MAX_N; }
 
 extern "C" size_t pcl_emd_workspace_bytes(int B, int N) {
     (void)N;
-    const size_t red = (size_t)RED_BLOCKS * 2 * sizeof(double), prof = ((size_t)(B > 0 ? B : 0) * 16 * 8 + 512) * sizeof(long long);
+    const size_t red = (size_t)RED_BLOCKS * 2 * sizeof(double), prof = ((size_t)(B > 0 ? B : 0) * 16 * 16 + 512) * sizeof(long long);
     size_t cold = 0;
     if (N > EMD_SMEM_ONLY_N && B > 0) {  // large clouds: per-CTA global region for the cold state, sized for the largest cluster
         int cs = 16;
@@ -916,7 +947,8 @@ extern "C" int pcl_emd_fwd(const void *xyz1, int dtype1, int64_t bs1, int64_t rs
     if (N <= EMD_SMEM_ONLY_N && emd_smem_bytes(N, flags | EMD_F_X1) <= (size_t)di.max_smem_optin) flags |= EMD_F_X1;
     if (getenv("PCL_EMD_NO_SORT")) flags &= ~EMD_F_SORT;  // development aid: natural order (no spatial pruning benefit)
     int pcap = 2 * EMD_THREADS;  // room for 32 work items with partials; fall back to 16 when shared memory is tight
-    if (emd_smem_bytes(N, flags, pcap) > (size_t)di.max_smem_optin) pcap = EMD_THREADS;
+    if (const char *e = getenv("PCL_EMD_PCAP")) pcap = atoi(e) * 32;  // development aid: work items with partials
+    while (pcap > EMD_THREADS && emd_smem_bytes(N, flags, pcap) > (size_t)di.max_smem_optin) pcap -= EMD_THREADS;
     const size_t smem = emd_smem_bytes(N, flags, pcap);
     int wpb_max = EMD_WPB_MAX;
     if (const char *e = getenv("PCL_EMD_WPB")) wpb_max = atoi(e);  // development aid
@@ -941,9 +973,9 @@ extern "C" int pcl_emd_fwd(const void *xyz1, int dtype1, int64_t bs1, int64_t rs
     at[0].val.clusterDim.x = cs; at[0].val.clusterDim.y = 1; at[0].val.clusterDim.z = 1;
     cfg.attrs = at; cfg.numAttrs = 1;
     const Pts p1{xyz1, bs1, rs1, dtype1}, p2{xyz2, bs2, rs2, dtype2};
-    // development aid: PCL_EMD_PROFILE=1 makes the workspace receive per-phase clock totals (B*cs*8 int64)
+    // development aid: PCL_EMD_PROFILE=1 makes the workspace receive per-phase clock totals (B*cs*16 int64)
     static const bool profile = getenv("PCL_EMD_PROFILE") != nullptr;
-    if (profile && !(flags & EMD_F_COLD) && workspace && workspace_bytes >= ((size_t)B * cs * 8 + 512) * sizeof(long long)) {
+    if (profile && !(flags & EMD_F_COLD) && workspace && workspace_bytes >= ((size_t)B * cs * 16 + 512) * sizeof(long long)) {
         PCL_CUDA(cudaLaunchKernelEx(&cfg, emd_auction_kernel<true>, p1, p2, N, eps, iters, flags, pcap, wpb_max, items_target, dist, (int *)assignment, (int *)stats, (long long *)workspace, (unsigned char *)nullptr));
     } else {
         PCL_CUDA(cudaLaunchKernelEx(&cfg, emd_auction_kernel<false>, p1, p2, N, eps, iters, flags, pcap, wpb_max, items_target, dist, (int *)assignment, (int *)stats, (long long *)nullptr, (unsigned char *)((flags & EMD_F_COLD) ? workspace : nullptr)));

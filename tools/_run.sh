@@ -1,3 +1,7 @@
-python -m pytest tests/test_chamfer_gpu.py -x -q 2>&1 | tail -2
-echo default; for n in 1024 2048 8192; do N=$n python tools/chamfer_time.py; done
-for v in vB vC vD vE vF vG vH; do echo $v; PCL_LIB_OVERRIDE=pointcloud_b200/_build/variants/$v.so python -m pytest tests/test_chamfer_gpu.py -x -q 2>&1 | tail -1; for n in 1024 2048 8192; do PCL_LIB_OVERRIDE=pointcloud_b200/_build/variants/$v.so N=$n python tools/chamfer_time.py; done; done
+python tools/emd_time.py base
+PCL_EMD_PCAP=64 PCL_EMD_ITEMS=48 python tools/emd_time.py items48
+PCL_EMD_PCAP=64 PCL_EMD_ITEMS=64 python tools/emd_time.py items64
+PCL_EMD_PCAP=96 PCL_EMD_ITEMS=96 python tools/emd_time.py items96
+PCL_EMD_PCAP=128 PCL_EMD_ITEMS=128 python tools/emd_time.py items128
+PCL_EMD_PCAP=64 PCL_EMD_ITEMS=64 PCL_EMD_WPB=64 python tools/emd_time.py items64_wpb64
+PCL_EMD_PCAP=64 PCL_EMD_ITEMS=64 PCL_EMD_WPB=128 python tools/emd_time.py items64_wpb128

@@ -7,7 +7,7 @@ import pointcloud_b200 as pcl
 from pointcloud_b200 import _lib, synth
 
 L = _lib.lib()
-names = ["init", "compact", "bid", "cluster_wait", "resolve", "epilogue"]
+names = ["init", "compact", "lpb_work", "cluster_wait", "resolve", "epilogue", "lpb_seeds", "publish", "wpb_work", "lpb_sync_merge"]
 for kind in ("uniform", "table", "noisy"):
     b, n = 32, 2048
     if kind == "uniform":
@@ -25,12 +25,14 @@ for kind in ("uniform", "table", "noisy"):
         assert rc == 0
     torch.cuda.synchronize()
     cs = int(stats[0, 3])
-    prof = ws.view(torch.int64)[: b * cs * 8].view(b, cs, 8).double().cpu()
+    prof = ws.view(torch.int64)[: b * cs * 16].view(b, cs, 16).double().cpu()
     tot = prof.sum(-1)
     print(f"{kind}: cs={cs} iters_run={stats[:,1].tolist()[:6]}.. per-CTA total cycles mean={tot.mean():.0f} max={tot.max():.0f}")
+    slow = int(tot.sum(1).argmax())
+    print(f"   per-cloud totals (Mcyc): {[round(float(v) / 1e6, 2) for v in tot.mean(1)]}  slowest cloud {slow}: " + ", ".join(f"{nm}={prof[slow,:,i].mean()/1e3:.0f}k" for i, nm in enumerate(names)))
     for i, nm in enumerate(names):
         print(f"   {nm:13s} mean {prof[:,:,i].mean():10.0f} cyc ({100*prof[:,:,i].mean()/tot.mean():5.1f}%)  max {prof[:,:,i].max():10.0f}")
     ev = (stats[:, 4].long() & 0xffffffff) + (stats[:, 5].long() << 32)
     print(f"   executed evals / algorithmic evals = {ev.sum().item() / (stats[:,0].long().sum().item() * n):.3f}")
-    it = ws.view(torch.int64)[b * cs * 8: b * cs * 8 + 200].view(50, 4).cpu().tolist()
+    it = ws.view(torch.int64)[b * cs * 16: b * cs * 16 + 200].view(50, 4).cpu().tolist()
     print("   per-iteration (U, bid cyc, KS*1000+Gn, wait cyc) of CTA0:", [tuple(int(v) for v in r) for r in it][:50])
