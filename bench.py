@@ -331,8 +331,10 @@ def main():
                 "executed_fraction": statistics.mean(executed) / evals,
                 "executed_note": "algorithmic = every (bidder, target) pair of the reference's Bid (N * sum_t U_t); the kernel proves "
                                  "whole 32-target tiles irrelevant with an exact bounding-box test and really evaluates only this fraction"}
-    # secondary roofline: the Chamfer forward kernel alone (FP32 CUDA-core bound as well; unfused arithmetic => at most 50 % of
-    # the FLOP peak because 8 FLOP occupy 8 FMA-pipe issue slots; ncu FMA-pipe utilisation 58 %: profiles/r1_final_chamfer_nn3_full.txt)
+    # secondary roofline: the Chamfer forward kernel alone (FP32 CUDA-core bound as well).  `achieved` counts the ALGORITHMIC 8 FLOP
+    # per directed evaluation; the kernel executes 3 FFMA2-halves (6 FLOP) per evaluation in its approximate scan and
+    # the exact arithmetic only for the candidate chunks, so `executed_fma_lane_ops_frac` (3 FMA-pipe lane-ops per evaluation against
+    # the 128 lanes/clk/SM) is the pipe utilisation the scan itself accounts for; ncu: profiles/r1_s2_chamfer_nn3_full.txt
     tch = []
     for i in range(min(K, 32)):
         p, t, _ = pool[(W + i) % n_sets]
@@ -351,7 +353,7 @@ def main():
     roofline_chamfer = {"kernel": "chamfer_nn3_kernel (+memset, finish)", "bound": "fp32-cuda-core", "achieved": ch_achieved, "peak": fp32_peak_tflops,
                         "unit": "TFLOP/s", "frac": ch_achieved / fp32_peak_tflops, "traffic": None, "avg_launch_ms": ch_ms,
                         "algorithmic": f"{FLOP_PER_CHAMFER_EVAL} FLOP x 2*B*N*M directed evaluations = {FLOP_PER_CHAMFER_EVAL * ch_evals:.3e} FLOP per launch",
-                        "fma_pipe_lane_ops_frac": 8 * ch_evals / (ch_ms * 1e-3) / (fp32_peak_tflops * 1e12 / 2)}
+                        "executed_fma_lane_ops_frac": 3 * ch_evals / (ch_ms * 1e-3) / (fp32_peak_tflops * 1e12 / 2)}
     breakdown = {k: statistics.mean(v) for k, v in phases.items()}
     breakdown["ms_per_step_independent"] = statistics.mean(per_regime["independent"]) if per_regime["independent"] else None
     breakdown["ms_per_step_noisy"] = statistics.mean(per_regime["noisy"]) if per_regime["noisy"] else None
