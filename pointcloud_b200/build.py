@@ -29,6 +29,19 @@ def needs_build() -> bool:
 def build(force: bool = False, verbose: bool = False) -> str:
     if not force and not needs_build():
         return LIB
+    # several ranks of one node may get here at the same time (torchrun on a fresh checkout): one builds, the others wait
+    import fcntl
+    with open(LIB + ".lock", "w") as lock:
+        fcntl.flock(lock, fcntl.LOCK_EX)
+        try:
+            if not force and not needs_build():
+                return LIB
+            return _build_locked(verbose)
+        finally:
+            fcntl.flock(lock, fcntl.LOCK_UN)
+
+
+def _build_locked(verbose: bool) -> str:
     objdir = os.path.join(HERE, "_build")
     os.makedirs(objdir, exist_ok=True)
     env = dict(os.environ)
@@ -50,8 +63,10 @@ def build(force: bool = False, verbose: bool = False) -> str:
         if p.returncode:
             raise RuntimeError(f"nvcc failed on {s}")
         objs.append(obj)
-    cmd = [_nvcc(), "-ccbin", ccbin, "-shared", "-gencode", "arch=compute_100a,code=sm_100a", "-o", LIB, *objs]
+    tmp = f"{LIB}.tmp{os.getpid()}"
+    cmd = [_nvcc(), "-ccbin", ccbin, "-shared", "-gencode", "arch=compute_100a,code=sm_100a", "-o", tmp, *objs]
     subprocess.run(cmd, check=True, env=env)
+    os.replace(tmp, LIB)  # atomic: a concurrent reader never sees a half-written library
     return LIB
 
 
