@@ -148,6 +148,39 @@ PCL_API int pcl_emd_weighted_bwd(const void *xyz1, int dtype1, int64_t bs1, int6
                          const int32_t *matched_label, const float *class_weights, int C,
                          const float *sums, const float *grad_out, float *grad_xyz1, void *stream);
 
+/*
+ * Feature term of EarthMoverDistance, fused (replaces the torch ops of pointcloud_vision/utils.py:278-279,293-301;
+ * SURVEY.md 8f row 2).  Both forward calls return (numerator, denominator) in sums[0..1] so that a batch-sharded caller
+ * can all-reduce them before dividing; accumulation is fp64 in a fixed order.  workspace >= pcl_emd_feature_workspace_bytes().
+ *
+ * pcl_emd_seg_ce_fwd (Segmenter, utils.py:293-295): logits (B,N,C) given as pointer + strides (pred[..., 3:]),
+ *   matched_label = labels of the matched targets (pcl_emd_match_hist), class_weights float[C]:
+ *   sums[0] = sum_i w_i * (logsumexp(logits_i) - logits_i[label_i]), sums[1] = sum_i w_i, w_i = class_weights[label_i]
+ *   (F.cross_entropy(..., weight=class_weights) == sums[0] / sums[1]).  pred_hist (nullable int64[C], zeroed by the
+ *   callee) receives the histogram of argmax_c logits (first maximum), the input of the logged KL term (utils.py:278-279).
+ *   C <= 64.
+ * pcl_emd_seg_ce_bwd: grad_logits (B,N,C) dense fp32 = grad_sums[0] * w_i * (softmax(logits_i) - onehot(label_i));
+ *   grad_sums is a DEVICE pointer (the upstream gradient of sums[0]).
+ * pcl_emd_feat_mse_fwd (Autoencoder, utils.py:257-258,301): sums[0] = sum (feat[b,i,f] - tfeat[b,assignment[b,i],f])^2,
+ *   sums[1] = B*N*F  (F.mse_loss of the prediction against the permuted target == sums[0] / sums[1]).
+ * pcl_emd_feat_mse_bwd: grad_feat (B,N,F) dense fp32 = grad_sums[0] * 2 * (feat - tfeat[assignment]).
+ */
+PCL_API size_t pcl_emd_feature_workspace_bytes(void);
+PCL_API int pcl_emd_seg_ce_fwd(const void *logits, int dtype, int64_t bs, int64_t rs, const int32_t *matched_label,
+                       const float *class_weights, int B, int N, int C, float *sums, int64_t *pred_hist,
+                       void *workspace, size_t workspace_bytes, void *stream);
+PCL_API int pcl_emd_seg_ce_bwd(const void *logits, int dtype, int64_t bs, int64_t rs, const int32_t *matched_label,
+                       const float *class_weights, int B, int N, int C, const float *grad_sums, float *grad_logits,
+                       void *stream);
+PCL_API int pcl_emd_feat_mse_fwd(const void *feat, int dtype1, int64_t bs1, int64_t rs1,
+                         const void *tfeat, int dtype2, int64_t bs2, int64_t rs2,
+                         const int32_t *assignment, int B, int N, int F, float *sums,
+                         void *workspace, size_t workspace_bytes, void *stream);
+PCL_API int pcl_emd_feat_mse_bwd(const void *feat, int dtype1, int64_t bs1, int64_t rs1,
+                         const void *tfeat, int dtype2, int64_t bs2, int64_t rs2,
+                         const int32_t *assignment, int B, int N, int F,
+                         const float *grad_sums, float *grad_feat, void *stream);
+
 /* ------------------------------------------------------------------ sampling ------ */
 /*
  * Farthest point sampling: replaces pointnet2_ops._ext.furthest_point_sampling (models/pointnet2_utils.py:6,89-90)

@@ -34,6 +34,11 @@ _SIGNATURES = {
     "pcl_emd_match_hist": (c_int, _PTS + [c_void_p, c_int, c_int, c_int, c_void_p, c_void_p, c_void_p]),
     "pcl_emd_weighted_reduce": (c_int, [c_void_p] * 3 + [c_int] * 3 + [c_void_p, c_void_p, c_size_t, c_void_p]),
     "pcl_emd_weighted_bwd": (c_int, _PTS + _PTS + [c_int, c_int] + [c_void_p] * 4 + [c_int] + [c_void_p] * 3 + [c_void_p]),
+    "pcl_emd_feature_workspace_bytes": (c_size_t, []),
+    "pcl_emd_seg_ce_fwd": (c_int, _PTS + [c_void_p, c_void_p, c_int, c_int, c_int, c_void_p, c_void_p, c_void_p, c_size_t, c_void_p]),
+    "pcl_emd_seg_ce_bwd": (c_int, _PTS + [c_void_p, c_void_p, c_int, c_int, c_int, c_void_p, c_void_p, c_void_p]),
+    "pcl_emd_feat_mse_fwd": (c_int, _PTS + _PTS + [c_void_p, c_int, c_int, c_int, c_void_p, c_void_p, c_size_t, c_void_p]),
+    "pcl_emd_feat_mse_bwd": (c_int, _PTS + _PTS + [c_void_p, c_int, c_int, c_int, c_void_p, c_void_p, c_void_p]),
     "pcl_fps_max_points": (c_int, []),
     "pcl_fps": (c_int, _PTS + [c_int, c_int, c_int, c_void_p, c_int, c_void_p, c_void_p]),
     "pcl_ball_query": (c_int, _PTS + _PTS + [c_int, c_int, c_int, c_float, c_int, c_void_p, c_void_p]),

@@ -147,6 +147,76 @@ def matched_label_hist(target_label, assignment, num_classes):
     return hist, matched
 
 
+class _SegCrossEntropySums(Function):
+    """(sum_i w_i nll_i, sum_i w_i) of the class-weighted cross entropy (utils.py:293-295) and the histogram of
+    argmax(logits) (utils.py:278-279), one kernel; backward: w_i (softmax - onehot), one kernel."""
+
+    @staticmethod
+    def forward(ctx, logits, matched, class_weights):
+        L = _lib.lib()
+        b, n, c = logits.shape
+        dev = logits.device
+        with torch.cuda.device(dev):
+            sums = torch.empty(2, device=dev, dtype=torch.float32)
+            pred_hist = torch.empty(c, device=dev, dtype=torch.int64)
+            wsb = L.pcl_emd_feature_workspace_bytes()
+            ws = torch.empty(wsb, device=dev, dtype=torch.uint8)
+            rc = L.pcl_emd_seg_ce_fwd(*_lib.pts_args(logits), matched.data_ptr(), class_weights.data_ptr(), b, n, c,
+                                      sums.data_ptr(), pred_hist.data_ptr(), ws.data_ptr(), wsb, _lib.stream_ptr())
+            _lib.check(rc, "pcl_emd_seg_ce_fwd")
+        ctx.save_for_backward(logits, matched, class_weights)
+        ctx.mark_non_differentiable(pred_hist)
+        return sums, pred_hist
+
+    @staticmethod
+    def backward(ctx, grad_sums, _grad_hist):
+        logits, matched, class_weights = ctx.saved_tensors
+        L = _lib.lib()
+        b, n, c = logits.shape
+        dev = logits.device
+        g = grad_sums.contiguous().float()
+        with torch.cuda.device(dev):
+            grad = torch.empty(b, n, c, device=dev, dtype=torch.float32)
+            rc = L.pcl_emd_seg_ce_bwd(*_lib.pts_args(logits), matched.data_ptr(), class_weights.data_ptr(), b, n, c,
+                                      g.data_ptr(), grad.data_ptr(), _lib.stream_ptr())
+            _lib.check(rc, "pcl_emd_seg_ce_bwd")
+        return grad.to(logits.dtype), None, None
+
+
+class _MatchedFeatureMSESums(Function):
+    """(sum (pred_feat - target_feat[assignment])^2, element count): F.mse_loss against the permuted target
+    (utils.py:257-258,301) without materialising the permutation; backward: 2 (pred_feat - target_feat[assignment])."""
+
+    @staticmethod
+    def forward(ctx, feat, tfeat, assignment):
+        L = _lib.lib()
+        b, n, f = feat.shape
+        dev = feat.device
+        with torch.cuda.device(dev):
+            sums = torch.empty(2, device=dev, dtype=torch.float32)
+            wsb = L.pcl_emd_feature_workspace_bytes()
+            ws = torch.empty(wsb, device=dev, dtype=torch.uint8)
+            rc = L.pcl_emd_feat_mse_fwd(*_lib.pts_args(feat), *_lib.pts_args(tfeat), assignment.data_ptr(), b, n, f,
+                                        sums.data_ptr(), ws.data_ptr(), wsb, _lib.stream_ptr())
+            _lib.check(rc, "pcl_emd_feat_mse_fwd")
+        ctx.save_for_backward(feat, tfeat, assignment)
+        return sums
+
+    @staticmethod
+    def backward(ctx, grad_sums):
+        feat, tfeat, assignment = ctx.saved_tensors
+        L = _lib.lib()
+        b, n, f = feat.shape
+        dev = feat.device
+        g = grad_sums.contiguous().float()
+        with torch.cuda.device(dev):
+            grad = torch.empty(b, n, f, device=dev, dtype=torch.float32)
+            rc = L.pcl_emd_feat_mse_bwd(*_lib.pts_args(feat), *_lib.pts_args(tfeat), assignment.data_ptr(), b, n, f,
+                                        g.data_ptr(), grad.data_ptr(), _lib.stream_ptr())
+            _lib.check(rc, "pcl_emd_feat_mse_bwd")
+        return grad.to(feat.dtype), None, None
+
+
 class EarthMoverDistance:
     """utils.py:245-309.  `fused=True` (default) computes the point term with the fused epilogue kernels
     (matched-label histogram, weighted sqrt-sum, fused backward); `fused=False` follows the reference's
@@ -183,15 +253,13 @@ class EarthMoverDistance:
             return self.reduce_ratio(num, den)
         return num / den
 
-    def _kl(self, pred, distribution):
-        pred_classes = pred[:, :, 3:].argmax(dim=2)                                  # utils.py:278
-        pred_hist = torch.bincount(pred_classes.view(-1), minlength=self.C)          # :279
+    def _kl(self, pred_hist, distribution):
         if self.reduce_hist is not None:
             pred_hist = self.reduce_hist(pred_hist)
-        pred_distribution = pred_hist / pred_hist.sum()                              # :280
+        pred_distribution = pred_hist / pred_hist.sum()                              # utils.py:280
         return F.kl_div(F.log_softmax(pred_distribution, dim=0), F.softmax(distribution, dim=0), reduction='batchmean')  # :283
 
-    # -- the three places where the fused path enters the CUDA library (overridden only by CPU host-logic tests)
+    # -- the places where the fused path enters the CUDA library (overridden only by CPU host-logic tests)
     def _auction(self, pred, target):
         xyz1, xyz2 = _lib.as_points(pred[:, :, :3]), _lib.as_points(target[:, :, :3])
         dists, assignment, _ = emd_forward_raw(xyz1, xyz2, self.eps, self.iterations)
@@ -202,6 +270,14 @@ class EarthMoverDistance:
 
     def _point_sums(self, xyz1, xyz2, dists, assignment, matched, class_weights):
         return _MatchedPointLoss.apply(xyz1, xyz2, dists, assignment, matched, class_weights)
+
+    def _ce_sums(self, pred, matched, class_weights):
+        """(sum w*nll, sum w) of the weighted cross entropy and the argmax histogram of the logits (utils.py:278-279,293-295)."""
+        return _SegCrossEntropySums.apply(_lib.as_points(pred[:, :, 3:]), matched, class_weights)
+
+    def _mse_sums(self, pred, target, assignment):
+        """(sum of squared feature differences against the permuted target, element count) (utils.py:257-258,301)."""
+        return _MatchedFeatureMSESums.apply(_lib.as_points(pred[:, :, 3:]), _lib.as_points(target[:, :, 3:]), assignment)
 
     def __call__(self, pred, target):
         if not self.fused:
@@ -220,27 +296,22 @@ class EarthMoverDistance:
         if self.C is not None:  # segmentation (utils.py:269-298)
             hist, matched = self._matched_hist(target, assignment)
             distribution, class_weights = self._class_weights(hist)
-            kl_div = self._kl(pred, distribution)
             class_weights = class_weights.float().contiguous()
-            target_classes = matched.long()
             # weighted cross entropy == sum_i w_i * nll_i / sum_i w_i  (F.cross_entropy with weight=, utils.py:295)
-            logp = F.log_softmax(pred[:, :, 3:].float(), dim=2)
-            nll = -logp.gather(2, target_classes.unsqueeze(-1)).squeeze(-1)
-            w = class_weights[target_classes]
-            ce_l = self._ratio((nll * w).sum(), w.sum())
+            ce_sums, pred_hist = self._ce_sums(pred, matched, class_weights)
+            kl_div = self._kl(pred_hist, distribution)
+            ce_l = self._ratio(ce_sums[0], ce_sums[1])
             feature_l = 0.1 * ce_l
             self.log('train_loss/cross_entropy', ce_l)
             self.log('train_loss/kl_divergence', kl_div)
             sums = self._point_sums(xyz1, xyz2, dists, assignment, matched, class_weights)
         else:  # general feature loss (utils.py:300-301)
-            idx = assignment.long().unsqueeze(-1)
-            matched_feat = target[:, :, 3:].take_along_dim(idx, 1)
-            diff = pred[:, :, 3:] - matched_feat
-            numel = diff.numel()
-            if numel == 0:
+            if pred.shape[2] == 3 or pred.numel() == 0:
+                matched_feat = target[:, :, 3:].take_along_dim(assignment.long().unsqueeze(-1), 1)
                 feature_l = F.mse_loss(pred[:, :, 3:], matched_feat)  # nan, exactly like the reference on empty features
             else:
-                feature_l = self._ratio((diff * diff).sum(), torch.tensor(float(numel), device=pred.device))
+                mse_sums = self._mse_sums(pred, target, assignment)
+                feature_l = self._ratio(mse_sums[0], mse_sums[1])
             sums = self._point_sums(xyz1, xyz2, dists, assignment, None, None)
 
         point_l = self._ratio(sums[0], sums[1])  # utils.py:304

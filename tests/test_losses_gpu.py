@@ -6,6 +6,7 @@ import ctypes
 import numpy as np
 import pytest
 import torch
+import torch.nn.functional as F
 
 import pointcloud_b200 as pcl
 from oracle import loss_oracle
@@ -227,3 +228,36 @@ def test_sharded_wrapper_single_rank_is_identity():
     a.backward(); b.backward()
     assert float(a) == pytest.approx(float(b), rel=1e-6)
     np.testing.assert_allclose(npy(p1.grad), npy(p2.grad), rtol=1e-6, atol=1e-12)
+
+
+def test_fused_feature_term_entry_points():
+    """pcl_emd_seg_ce_fwd/bwd and pcl_emd_feat_mse_fwd/bwd against plain torch on strided fp32 / bf16 views
+    (utils.py:278-279,293-301): sums and gradients within 1e-5 relative, argmax histogram exact."""
+    from pointcloud_b200.losses import _MatchedFeatureMSESums, _SegCrossEntropySums
+    g = torch.Generator().manual_seed(31)
+    b, n, c = 3, 777, 5
+    pred = torch.randn(b, n, 3 + c, generator=g).cuda()
+    matched = torch.randint(0, c, (b, n), generator=g).int().cuda()
+    cw = torch.rand(c, generator=g).cuda() + 0.1
+    for dt in (torch.float32, torch.bfloat16):
+        p = pred.detach().to(dt).clone().requires_grad_()
+        sums, hist = _SegCrossEntropySums.apply(p[:, :, 3:], matched, cw)
+        (sums[0] / sums[1] * 0.7).backward()
+        q = pred.detach().to(dt).float().clone().requires_grad_()
+        ref = F.cross_entropy(q[:, :, 3:].permute(0, 2, 1), matched.long(), weight=cw)
+        (ref * 0.7).backward()
+        assert float(sums[0] / sums[1]) == pytest.approx(float(ref), rel=REL)
+        assert torch.equal(hist, torch.bincount(q[:, :, 3:].argmax(2).view(-1), minlength=c))
+        tol = REL if dt == torch.float32 else 1e-2   # bf16: the gradient itself is rounded to bf16
+        np.testing.assert_allclose(npy(p.grad.float()), npy(q.grad), rtol=tol, atol=1e-9 if dt == torch.float32 else 1e-7)
+    # matched-feature MSE (Autoencoder): pred (B,N,6), target (B,N,6) permuted by a non-bijective assignment
+    predf = torch.rand(b, n, 6, generator=g).cuda().requires_grad_()
+    target = torch.rand(b, n, 6, generator=g).cuda()
+    asg = torch.randint(0, n, (b, n), generator=g).int().cuda()
+    s2 = _MatchedFeatureMSESums.apply(predf[:, :, 3:], target[:, :, 3:], asg)
+    (s2[0] / s2[1]).backward()
+    q = predf.detach().clone().requires_grad_()
+    ref = F.mse_loss(q[:, :, 3:], target.take_along_dim(asg.long().unsqueeze(-1), 1)[:, :, 3:])
+    ref.backward()
+    assert float(s2[0] / s2[1]) == pytest.approx(float(ref), rel=REL) and float(s2[1]) == b * n * 3
+    np.testing.assert_allclose(npy(predf.grad), npy(q.grad), rtol=REL, atol=1e-10)

@@ -21,7 +21,7 @@ from pointcloud_b200.sharded import ShardedLoss, shard_bounds  # noqa: E402
 
 
 class CpuEMD(EarthMoverDistance):
-    """EarthMoverDistance with its three kernel entry points served by the CPU oracle (tests only)."""
+    """EarthMoverDistance with its kernel entry points served by the CPU oracle / plain torch (tests only)."""
 
     def _auction(self, pred, target):
         xyz1, xyz2 = pred[:, :, :3], target[:, :, :3]
@@ -37,6 +37,18 @@ class CpuEMD(EarthMoverDistance):
         d = ((xyz1 - m) ** 2).sum(-1)
         w = torch.ones_like(d) if class_weights is None else class_weights[matched.long()]
         return torch.stack([(d.sqrt() * w).sum(), w.sum()])
+
+
+    def _ce_sums(self, pred, matched, class_weights):
+        logp = torch.log_softmax(pred[:, :, 3:].float(), dim=2)
+        nll = -logp.gather(2, matched.long().unsqueeze(-1)).squeeze(-1)
+        w = class_weights[matched.long()]
+        pred_hist = torch.bincount(pred[:, :, 3:].argmax(dim=2).view(-1), minlength=self.C)
+        return torch.stack([(nll * w).sum(), w.sum()]), pred_hist
+
+    def _mse_sums(self, pred, target, assignment):
+        diff = pred[:, :, 3:] - target[:, :, 3:].take_along_dim(assignment.long().unsqueeze(-1), 1)
+        return torch.stack([(diff * diff).sum(), torch.tensor(float(diff.numel()))])
 
 
 class CpuChamfer(ChamferDistance):
