@@ -396,10 +396,12 @@ emd_auction_kernel(Pts xyz1, Pts xyz2, int N, float eps, int iters, int flags, i
         // ---- 1. list of unassigned bidders (emd_cuda.cu:23-93), ascending, identical in every CTA -------
         if (t > 0) {  // prices moved in the previous iteration: refresh the per-tile upper bound of c (same barrier interval)
             for (int tl = wid; tl < NT; tl += EMD_WARPS) {
-                float c = S.tgt[tl * TILE + lane].w;
-#pragma unroll
-                for (int o = 16; o > 0; o >>= 1) c = fmaxf(c, __shfl_xor_sync(0xffffffffu, c, o));
-                if (lane == 0) S.tlo[tl].w = c;
+                // warp maximum with one REDUX on an order-preserving integer image of the float (c may be negative: padding)
+                int b = __float_as_int(S.tgt[tl * TILE + lane].w);
+                b ^= (b >> 31) & 0x7fffffff;
+                b = __reduce_max_sync(0xffffffffu, b);
+                b ^= (b >> 31) & 0x7fffffff;
+                if (lane == 0) S.tlo[tl].w = __int_as_float(b);
             }
         }
         unsigned fl = 0;
@@ -699,29 +701,21 @@ emd_auction_kernel(Pts xyz1, Pts xyz2, int N, float eps, int iters, int flags, i
             const uint2 pb = pub_cur[jp];
             const int o = (int)(pb.x & 0xffffu);
             const double bi = (double)__uint_as_float(pb.y), mi = (double)S.maxinc[o];
-            if (bi - 1e-6 <= mi && mi <= bi + 1e-6)  // :188-191; the largest ORIGINAL bidder index wins
+            if (bi - 1e-6 <= mi && mi <= bi + 1e-6) {  // :188-191; the largest ORIGINAL bidder index wins
                 atomicMax(&S.maxidx[o], S.pperm ? (int)S.pperm[jp] : jp);
-        }
-        __syncthreads();
-        // decisions are all taken before any state is modified (U <= 4096 => at most 8 passes per thread)
-        unsigned winmask = 0;
-        for (int q = tid, p = 0; q < U; q += T, p++) {
-            const int jp = S.unass[q];
-            const uint2 pb = pub_cur[jp];
-            const int o = (int)(pb.x & 0xffffu);
-            const bool winner = (S.maxidx[o] == (S.pperm ? (int)S.pperm[jp] : jp));
-            if (last || winner) winmask |= 1u << p;  // emd_cuda.cu:201
-            if (!winner && rank == 0) {               // statistics only: bidders inside the window that lost the race
-                const double bi = (double)__uint_as_float(pb.y), mi = (double)S.maxinc[o];
-                if (bi - 1e-6 <= mi && mi <= bi + 1e-6) extra_qualifiers++;
+                extra_qualifiers += (rank == 0) ? 1 : 0;  // statistics: bidders inside the window (the winners are subtracted below)
             }
         }
         __syncthreads();
-        for (int q = tid, p = 0; q < U; q += T, p++) {
-            if (!((winmask >> p) & 1u)) continue;
+        // Decide and commit in one pass: a decision reads only max_idx[o], which nobody but the winner of o writes again
+        // (its reset to -1 makes every later reader of o a non-winner, which is what it is).
+        for (int q = tid; q < U; q += T) {
             const int jp = S.unass[q];
             const uint2 pb = pub_cur[jp];
             const int o = (int)(pb.x & 0xffffu);  // emd_cuda.cu:203-211
+            const bool winner = (S.maxidx[o] == (S.pperm ? (int)S.pperm[jp] : jp));
+            extra_qualifiers -= (winner && rank == 0) ? 1 : 0;
+            if (!(last || winner)) continue;      // emd_cuda.cu:201
             const unsigned prev = S.inv[o];
             if (!last && prev != NONE16) S.asg[prev] = NONE16;
             S.inv[o] = (unsigned short)jp;
