@@ -503,6 +503,8 @@ emd_auction_kernel(Pts xyz1, Pts xyz2, int N, float eps, int iters, int flags, i
                 const float3 a = pred_xyz(jp);
                 unsigned lp = S.last[jp], lp34 = S.last34[jp];
                 if (flags & EMD_F_SORT) first_seeds(jp, N, lp, lp34);
+                long long wb0 = 0; int ncand = 0, nrounds = 0, nsteps = 0;
+                if constexpr (PROF) wb0 = clock64();
                 float tm = -1e9f;
                 {
                     const int k1 = (int)(lp & 0xffffu), k2 = (int)(lp >> 16);
@@ -527,6 +529,7 @@ emd_auction_kernel(Pts xyz1, Pts xyz2, int N, float eps, int iters, int flags, i
                     bool cand = false;
                     if (tl < NT) cand = !tile_skippable(S.tlo[tl], S.thi[tl], a.x, a.y, a.z, tm);
                     unsigned cm = __ballot_sync(0xffffffffu, cand);
+                    if constexpr (PROF) ncand += __popc(cm);
                     constexpr int WC = PCL_WPB_CHUNK;
                     while (cm) {  // up to WC candidate tiles per step: WC independent filter chains per lane, one vote
                         int tix[WC];
@@ -552,6 +555,7 @@ emd_auction_kernel(Pts xyz1, Pts xyz2, int N, float eps, int iters, int flags, i
 #pragma unroll
                             for (int i = 0; i < WC; i++) my_evals += have[i] ? TILE : 0;
                         }
+                        if constexpr (PROF) nsteps++;
                         if (!__any_sync(0xffffffffu, any)) continue;
                         // Every lane takes ITS first surviving slot, so that one pass through the sqrt/F2F/DADD chain serves
                         // all lanes (a lane rarely has two survivors among its 4 targets; leftovers loop).
@@ -569,6 +573,7 @@ emd_auction_kernel(Pts xyz1, Pts xyz2, int N, float eps, int iters, int flags, i
                             int ko = 0;
                             if (sel >= 0) { v = bid_value_exact(ssel, S.pf[ksel]); ko = S.tperm ? (int)S.tperm[ksel] : ksel; }
                             unsigned pm = __ballot_sync(0xffffffffu, sel >= 0);
+                            if constexpr (PROF) nrounds += 1 + (__popc(pm) << 8);
                             while (pm) {
                                 const int l = __ffs(pm) - 1;
                                 pm &= pm - 1;
@@ -587,6 +592,13 @@ emd_auction_kernel(Pts xyz1, Pts xyz2, int N, float eps, int iters, int flags, i
                 }
                 if (lane == 0) publish(jp, best, better, (unsigned)(bi & 0xffff) | ((unsigned)(bi2 & 0xffff) << 16),
                                        (unsigned)(k3 & 0xffff) | ((unsigned)(k4 & 0xffff) << 16));
+                if constexpr (PROF) {  // slowest warp-per-bidder scan of this CTA and iteration: cycles | candidate tiles | steps | exact rounds | survivors
+                    if (lane == 0 && prof && blockIdx.x < 4 && t < 50) {
+                        const unsigned long long v = ((unsigned long long)(clock64() - wb0) << 40) | ((unsigned long long)(ncand & 0xff) << 32) |
+                                                     ((unsigned long long)(nsteps & 0xff) << 24) | ((unsigned long long)(nrounds & 0xff) << 16) | (unsigned long long)((nrounds >> 8) & 0xffff);
+                        atomicMax((unsigned long long *)&prof[(size_t)gridDim.x * 16 + 256 + blockIdx.x * 50 + t], v);
+                    }
+                }
             }
             PCL_TICK(8)
         } else {

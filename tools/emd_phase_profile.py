@@ -36,3 +36,10 @@ for kind in ("uniform", "table", "noisy"):
     print(f"   executed evals / algorithmic evals = {ev.sum().item() / (stats[:,0].long().sum().item() * n):.3f}")
     it = ws.view(torch.int64)[b * cs * 16: b * cs * 16 + 200].view(50, 4).cpu().tolist()
     print("   per-iteration (U, bid cyc, KS*1000+Gn, wait cyc) of CTA0:", [tuple(int(v) for v in r) for r in it][:50])
+    hb = ws.view(torch.int64)[b * cs * 16 + 256: b * cs * 16 + 256 + 200].view(4, 50).cpu()
+    rows = []
+    for t in range(0, 50):
+        best = max(int(hb[c, t]) for c in range(4))
+        if best:
+            rows.append((t, best >> 40, (best >> 32) & 0xff, (best >> 24) & 0xff, (best >> 16) & 0xff, best & 0xffff))
+    print("   slowest warp-per-bidder scan per iteration of cloud 0 (t, cycles, candidate tiles, steps, exact rounds, survivors):", rows)
