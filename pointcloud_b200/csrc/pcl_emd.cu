@@ -574,6 +574,36 @@ emd_auction_kernel(Pts xyz1, Pts xyz2, int N, float eps, int iters, int flags, i
                             if (sel >= 0) { v = bid_value_exact(ssel, S.pf[ksel]); ko = S.tperm ? (int)S.tperm[ksel] : ksel; }
                             unsigned pm = __ballot_sync(0xffffffffu, sel >= 0);
                             if constexpr (PROF) nrounds += 1 + (__popc(pm) << 8);
+                            if (__popc(pm) > 3) {
+                                // Many survivors (a weak threshold, e.g. after an eviction): only the two largest of them can change
+                                // (best, better), so pick those with warp reductions instead of folding every survivor serially.
+                                // Largest value, lowest ORIGINAL index among equal maxima; then the largest of the remaining lanes
+                                // (duplicates of the maximum count, as in the serial rule).  NaN never updates anything: left out.
+                                const float vc = __fadd_rn(v, 0.f);  // -0 -> +0: equal floats get equal keys
+                                int key = __float_as_int(vc);
+                                key ^= (key >> 31) & 0x7fffffff;
+                                if (!(sel >= 0 && vc == vc)) key = (int)0x80000000;
+                                const int key1 = __reduce_max_sync(0xffffffffu, key);
+                                if (key1 != (int)0x80000000) {
+                                    const int ko1 = __reduce_min_sync(0xffffffffu, (key == key1) ? ko : 0x7fffffff);
+                                    const int l1 = __ffs(__ballot_sync(0xffffffffu, key == key1 && ko == ko1)) - 1;
+                                    const int keyr = (lane == l1) ? (int)0x80000000 : key;
+                                    const int key2 = __reduce_max_sync(0xffffffffu, keyr);
+                                    const int l2 = (key2 != (int)0x80000000) ? __ffs(__ballot_sync(0xffffffffu, keyr == key2)) - 1 : l1;
+                                    const float va = __shfl_sync(0xffffffffu, v, l1), vb = __shfl_sync(0xffffffffu, v, l2);
+                                    const int ka = __shfl_sync(0xffffffffu, ksel, l1), kb = __shfl_sync(0xffffffffu, ksel, l2);
+                                    const int kob = __shfl_sync(0xffffffffu, ko, l2);
+                                    if (va > best || (va == best && ko1 < bio)) { k4 = k3; k3 = bi2; better = best; bi2 = bi; best = va; bi = ka; bio = ko1; }
+                                    else if (va > better) { k4 = k3; k3 = bi2; better = va; bi2 = ka; }
+                                    else { k4 = k3; k3 = ka; }
+                                    if (key2 != (int)0x80000000) {
+                                        if (vb > best || (vb == best && kob < bio)) { k4 = k3; k3 = bi2; better = best; bi2 = bi; best = vb; bi = kb; bio = kob; }
+                                        else if (vb > better) { k4 = k3; k3 = bi2; better = vb; bi2 = kb; }
+                                        else { k4 = k3; k3 = kb; }
+                                    }
+                                }
+                                pm = 0;
+                            }
                             while (pm) {
                                 const int l = __ffs(pm) - 1;
                                 pm &= pm - 1;
