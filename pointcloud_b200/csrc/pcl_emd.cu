@@ -540,13 +540,14 @@ emd_auction_kernel(Pts xyz1, Pts xyz2, int N, float eps, int iters, int flags, i
                             tix[i] = tb + (have[i] ? __ffs(cm) - 1 : 0);
                             cm &= cm - 1;  // cm == 0 stays 0
                         }
-                        float sq[WC];
+                        float sq[WC], cw[WC];
                         bool pass[WC];
                         bool any = false;
 #pragma unroll
                         for (int i = 0; i < WC; i++) {
                             const float4 tq = S.tgt[tix[i] * TILE + lane];
                             sq[i] = sq3_ref(__fsub_rn(tq.x, a.x), __fsub_rn(tq.y, a.y), __fsub_rn(tq.z, a.z));
+                            cw[i] = tq.w;
                             const float u = __fsub_rn(tq.w, tm);
                             pass[i] = have[i] && !(__fmaf_rn(u, u, -sq[i]) < 0.f);
                             any |= pass[i];
@@ -613,11 +614,15 @@ emd_auction_kernel(Pts xyz1, Pts xyz2, int N, float eps, int iters, int flags, i
                                 else if (vl > better) { k4 = k3; k3 = bi2; better = vl; bi2 = kl; }
                                 else { k4 = k3; k3 = kl; }
                             }
+                            tm = fmaxf(tm, __fsub_rn(better, FILTER_MARGIN));  // re-test the leftovers against the tightened threshold
                             any = false;
 #pragma unroll
-                            for (int i = 0; i < WC; i++) any |= pass[i];
+                            for (int i = 0; i < WC; i++) {
+                                const float u = __fsub_rn(cw[i], tm);
+                                pass[i] = pass[i] && !(__fmaf_rn(u, u, -sq[i]) < 0.f);
+                                any |= pass[i];
+                            }
                         } while (__any_sync(0xffffffffu, any));
-                        tm = fmaxf(tm, __fsub_rn(better, FILTER_MARGIN));
                     }
                 }
                 if (lane == 0) publish(jp, best, better, (unsigned)(bi & 0xffff) | ((unsigned)(bi2 & 0xffff) << 16),
