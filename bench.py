@@ -34,7 +34,7 @@ WORKLOAD = ("config2: Chamfer+EMD fwd+bwd, B=32 per GPU, N=M=2048, Table-shaped 
             "regimes independent/noisy alternating, eps=0.005, iters=50")
 FLOP_PER_EMD_EVAL = 11   # 8 (distance) + sqrt + 2 adds
 FLOP_PER_CHAMFER_EVAL = 8
-NCU_AUCTION_DRAM_BYTES = 1657856  # ncu --set full, one launch (profiles/r1_final_emd_auction_full.txt)
+NCU_AUCTION_DRAM_BYTES = 1660416  # ncu --set full, one launch (profiles/r1_s2_emd_auction_full.txt)
 
 
 def peaks():
@@ -322,7 +322,7 @@ def main():
     achieved = FLOP_PER_EMD_EVAL * evals / (emd_ms * 1e-3) / 1e12
     roofline = {"kernel": "emd_auction_kernel", "bound": "fp32-cuda-core", "achieved": achieved, "peak": fp32_peak_tflops,
                 "unit": "TFLOP/s", "frac": achieved / fp32_peak_tflops, "traffic": NCU_AUCTION_DRAM_BYTES,
-                "traffic_source": "dram__bytes_read.sum + dram__bytes_write.sum of one launch, profiles/r1_final_emd_auction_full.txt "
+                "traffic_source": "dram__bytes_read.sum + dram__bytes_write.sum of one launch, profiles/r1_s2_emd_auction_full.txt "
                                   "(algorithmic: 1.57 MB inputs + 0.52 MB outputs; the auction state never leaves shared memory)",
                 "peak_source": f"{sm_count.value} SMs x 128 lanes x 2 FLOP x {sm_max:.0f} MHz (MEASURED_PEAKS.json sm_max_mhz); "
                                "contraction depth 3 => CUDA-core bound, neither hbm nor tensor (SURVEY.md 8d)",
