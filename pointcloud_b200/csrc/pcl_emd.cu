@@ -285,7 +285,7 @@ emd_auction_kernel(Pts xyz1, Pts xyz2, int N, float eps, int iters, int flags, i
     if constexpr (PROF) pc = clock64();
     extern __shared__ __align__(16) unsigned char smem_raw[];
     cg::cluster_group cluster = cg::this_cluster();
-    const int cs = (int)cluster.num_blocks(), rank = (int)cluster.block_rank();
+    const int cs = (int)cluster.num_blocks(), rank = (int)cluster.block_rank(), csl = __ffs(cs) - 1;  // cs is a power of two
     const int cloud = blockIdx.x / cs;
     const int tid = threadIdx.x, T = EMD_THREADS, lane = tid & 31, wid = tid >> 5;
     const size_t cold_stride = (emd_cold_bytes(N) + 255) / 256 * 256;
@@ -395,13 +395,23 @@ emd_auction_kernel(Pts xyz1, Pts xyz2, int N, float eps, int iters, int flags, i
         const bool last = (t == iters - 1);
         // ---- 1. list of unassigned bidders (emd_cuda.cu:23-93), ascending, identical in every CTA -------
         if (t > 0) {  // prices moved in the previous iteration: refresh the per-tile upper bound of c (same barrier interval)
-            for (int tl = wid; tl < NT; tl += EMD_WARPS) {
+            for (int t0 = wid; t0 < NT; t0 += 4 * EMD_WARPS) {  // four independent tiles per trip
                 // warp maximum with one REDUX on an order-preserving integer image of the float (c may be negative: padding)
-                int b = __float_as_int(S.tgt[tl * TILE + lane].w);
-                b ^= (b >> 31) & 0x7fffffff;
-                b = __reduce_max_sync(0xffffffffu, b);
-                b ^= (b >> 31) & 0x7fffffff;
-                if (lane == 0) S.tlo[tl].w = __int_as_float(b);
+                int b[4];
+#pragma unroll
+                for (int i = 0; i < 4; i++) {
+                    const int tl = min(t0 + i * EMD_WARPS, NT - 1);
+                    b[i] = __float_as_int(S.tgt[tl * TILE + lane].w);
+                    b[i] ^= (b[i] >> 31) & 0x7fffffff;
+                }
+#pragma unroll
+                for (int i = 0; i < 4; i++) b[i] = __reduce_max_sync(0xffffffffu, b[i]);
+#pragma unroll
+                for (int i = 0; i < 4; i++) {
+                    const int tl = t0 + i * EMD_WARPS;
+                    b[i] ^= (b[i] >> 31) & 0x7fffffff;
+                    if (lane == 0 && tl < NT) S.tlo[tl].w = __int_as_float(b[i]);
+                }
             }
         }
         unsigned fl = 0;
@@ -436,7 +446,7 @@ emd_auction_kernel(Pts xyz1, Pts xyz2, int N, float eps, int iters, int flags, i
             U += v;
         }
         if (U == 0) break;  // uniform across the cluster: replicas are identical
-        if (tid == 0) *work_ctr = 0;
+        if (tid == 0) *work_ctr = EMD_WARPS;  // the first work item of warp w is item w (no atomic on the critical path), the rest is dynamic
         {
             int pos = wbase + incl - cnt;
             const int base = tid * E;
@@ -458,17 +468,19 @@ emd_auction_kernel(Pts xyz1, Pts xyz2, int N, float eps, int iters, int flags, i
         // The (spatially sorted) list is dealt to the CTAs of the cluster in an interleaved way -- single bidders when
         // there are few (warp-per-bidder mode), blocks of 32 neighbours otherwise -- so that every CTA sees the
         // same mix of easy and hard regions.  list position of local bidder b:  pos(b).
-        const bool wpb = (U > 0 && (U + cs - 1) / cs <= wpb_max);
-        const int gsz = wpb ? 1 : 32;                       // dealing granularity
-        const int nblk = (U + gsz - 1) / gsz;               // blocks in the list
-        const int myblk = (nblk > rank) ? (nblk - rank + cs - 1) / cs : 0;  // blocks rank, rank+cs, ...
-        int Uc = myblk * gsz;
-        if (myblk > 0 && (rank + (myblk - 1) * cs) == nblk - 1) Uc -= nblk * gsz - U;  // the last block may be short
-        auto pos = [&](int b) -> int { return ((b / gsz) * cs + rank) * gsz + (b % gsz); };
+        // (cluster size and dealing granularity are powers of two: shifts instead of integer divisions, which every thread
+        // would otherwise execute in every iteration)
+        const bool wpb = (U > 0 && ((U + cs - 1) >> csl) <= wpb_max);
+        const int gsl = wpb ? 0 : 5, gsz = 1 << gsl;        // dealing granularity: 1 or 32 bidders
+        const int nblk = (U + gsz - 1) >> gsl;              // blocks in the list
+        const int myblk = (nblk > rank) ? ((nblk - rank + cs - 1) >> csl) : 0;  // blocks rank, rank+cs, ...
+        int Uc = myblk << gsl;
+        if (myblk > 0 && (rank + (myblk - 1) * cs) == nblk - 1) Uc -= (nblk << gsl) - U;  // the last block may be short
+        auto pos = [&](int b) -> int { return ((((b >> gsl) << csl) + rank) << gsl) + (b & (gsz - 1)); };
         const int Gn = (Uc + 31) >> 5;                                   // bidder groups (warps' worth)
         // tile slices per group: aim at ~2 work items per warp (dynamic queue), bounded by the partial buffer
         int KS = 1;
-        if (Gn > 0 && Gn < items_target) KS = max(1, min(min((items_target + Gn - 1) / Gn, NT), pcap / (Gn * 32)));
+        if (!wpb && Gn > 0 && Gn < items_target) KS = max(1, min(min((items_target + Gn - 1) / Gn, NT), pcap / (Gn * 32)));
         const int GS = Gn * 32;                                          // partial stride of one slice
         uint2 *pub_cur = S.pub + cur * n8;
 
@@ -494,10 +506,7 @@ emd_auction_kernel(Pts xyz1, Pts xyz2, int N, float eps, int iters, int flags, i
             // ---- few bidders: one WARP per bidder, one lane per target of a tile.  The tile tests are exact per
             // bidder (no other lane's neighbourhood keeps a tile alive), 32 boxes are tested per ballot, and the
             // rare candidates are folded into a warp-uniform top 2 in any order (the update is order-independent).
-            for (;;) {
-                int b = 0;
-                if (lane == 0) b = atomicAdd(work_ctr, 1);
-                b = __shfl_sync(0xffffffffu, b, 0);
+            for (int b = wid;;) {
                 if (b >= Uc) break;
                 const int jp = S.unass[pos(b)];
                 const float3 a = pred_xyz(jp);
@@ -634,6 +643,8 @@ emd_auction_kernel(Pts xyz1, Pts xyz2, int N, float eps, int iters, int flags, i
                         atomicMax((unsigned long long *)&prof[(size_t)gridDim.x * 16 + 256 + blockIdx.x * 50 + t], v);
                     }
                 }
+                if (lane == 0) b = atomicAdd(work_ctr, 1);  // next bidder of this warp
+                b = __shfl_sync(0xffffffffu, b, 0);
             }
             PCL_TICK(8)
         } else {
@@ -648,10 +659,7 @@ emd_auction_kernel(Pts xyz1, Pts xyz2, int N, float eps, int iters, int flags, i
         }
         __syncthreads();
         PCL_TICK(6)
-        for (;;) {
-            int it = 0;
-            if (lane == 0) it = atomicAdd(work_ctr, 1);
-            it = __shfl_sync(0xffffffffu, it, 0);
+        for (int it = wid;;) {
             if (it >= Gn * KS) break;
             const int g = it % Gn, sl = it / Gn;
             const int b = min(g * 32 + lane, Uc - 1);          // surplus lanes shadow the last bidder (results discarded)
@@ -677,6 +685,8 @@ emd_auction_kernel(Pts xyz1, Pts xyz2, int N, float eps, int iters, int flags, i
             } else if (active) {
                 S.pbest[sl * GS + b] = r.best; S.pbetter[sl * GS + b] = r.better; S.pbi[sl * GS + b] = pack; S.pbi34[sl * GS + b] = pack34;
             }
+            if (lane == 0) it = atomicAdd(work_ctr, 1);  // next work item of this warp
+            it = __shfl_sync(0xffffffffu, it, 0);
         }
         PCL_TICK(2)
         }
