@@ -250,6 +250,7 @@ def main():
     torch.cuda.set_device(local)
     device = torch.device("cuda", local)
     if world > 1:
+        os.environ.setdefault("NCCL_DEBUG_FILE", "/dev/stderr")  # NCCL's own log lines must not precede the JSON line on stdout
         dist.init_process_group("nccl", device_id=device)
 
     def barrier():
