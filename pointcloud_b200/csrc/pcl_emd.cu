@@ -389,6 +389,7 @@ emd_auction_kernel(Pts xyz1, Pts xyz2, int N, float eps, int iters, int flags, i
     long long sum_u = 0;
     unsigned long long my_evals = 0ull;  // evaluations this lane really executed (tiles that were not skipped)
     int iters_run = 0, extra_qualifiers = 0, cur = 0;
+    bool have_list = false;  // the list of unassigned bidders of the next iteration already exists (written during the commit)
     const int E = (n8 / 8 + T - 1) / T * 8;  // contiguous elements per thread in the compaction (multiple of 8, <= 32)
 
     for (int t = 0; t < iters; t++) {
@@ -414,6 +415,14 @@ emd_auction_kernel(Pts xyz1, Pts xyz2, int N, float eps, int iters, int flags, i
                 }
             }
         }
+        int U = 0;
+        if (have_list) {
+            // At most 32 bidders were left: warp 0 wrote the next list (the losers in list order, then the evicted owners)
+            // while it committed the bids -- identical in every CTA, and the dealing does not need it sorted.
+            U = S.wsum[40];
+            if (U == 0) break;
+            if (tid == 0) *work_ctr = EMD_WARPS;
+        } else {
         unsigned fl = 0;
         {
             const int base = tid * E;
@@ -438,7 +447,7 @@ emd_auction_kernel(Pts xyz1, Pts xyz2, int N, float eps, int iters, int flags, i
         }
         if (lane == 31) S.wsum[wid] = incl;
         __syncthreads();
-        int wbase = 0, U = 0;
+        int wbase = 0;
 #pragma unroll
         for (int w = 0; w < EMD_WARPS; w++) {
             const int v = S.wsum[w];
@@ -455,6 +464,7 @@ emd_auction_kernel(Pts xyz1, Pts xyz2, int N, float eps, int iters, int flags, i
                 fl &= fl - 1;
                 S.unass[pos++] = (unsigned short)(base + e);
             }
+        }
         }
         __syncthreads();
         sum_u += U;
@@ -766,15 +776,17 @@ emd_auction_kernel(Pts xyz1, Pts xyz2, int N, float eps, int iters, int flags, i
         __syncthreads();
         // Decide and commit in one pass: a decision reads only max_idx[o], which nobody but the winner of o writes again
         // (its reset to -1 makes every later reader of o a non-winner, which is what it is).
+        unsigned keep = NONE16;  // with at most 32 bidders (one per lane of warp 0): the bidder this lane leaves unassigned
+        bool loser = false;
         for (int q = tid; q < U; q += T) {
             const int jp = S.unass[q];
             const uint2 pb = pub_cur[jp];
             const int o = (int)(pb.x & 0xffffu);  // emd_cuda.cu:203-211
             const bool winner = (S.maxidx[o] == (S.pperm ? (int)S.pperm[jp] : jp));
             extra_qualifiers -= (winner && rank == 0) ? 1 : 0;
-            if (!(last || winner)) continue;      // emd_cuda.cu:201
+            if (!(last || winner)) { keep = (unsigned)jp; loser = true; continue; }  // emd_cuda.cu:201: a loser stays unassigned
             const unsigned prev = S.inv[o];
-            if (!last && prev != NONE16) S.asg[prev] = NONE16;
+            if (!last && prev != NONE16) { S.asg[prev] = NONE16; keep = prev; }  // the evicted owner becomes unassigned
             S.inv[o] = (unsigned short)jp;
             S.asg[jp] = (unsigned short)o;
             const float pnew = __fadd_rn(S.pf[o], __uint_as_float(pb.y));
@@ -782,6 +794,16 @@ emd_auction_kernel(Pts xyz1, Pts xyz2, int N, float eps, int iters, int flags, i
             S.tgt[o].w = __fsub_ru(3.0f, pnew);  // c = RU(3 - price): upper bound used by the filter
             S.maxinc[o] = -1e9f;
             S.maxidx[o] = -1;
+        }
+        have_list = (U <= 32);
+        if (have_list && wid == 0) {  // losers in list order, then evicted owners in list order: ballot compaction inside warp 0
+            const unsigned lose = __ballot_sync(0xffffffffu, loser);
+            const unsigned evic = __ballot_sync(0xffffffffu, keep != NONE16) & ~lose;
+            const unsigned below = (1u << lane) - 1u;
+            const int p = ((lose >> lane) & 1u) ? __popc(lose & below) : __popc(lose) + __popc(evic & below);
+            __syncwarp();  // every lane has read its entry of the old list
+            if (keep != NONE16) S.unass[p] = (unsigned short)keep;
+            if (lane == 0) S.wsum[40] = __popc(lose) + __popc(evic);
         }
         __syncthreads();
         cur ^= 1;
