@@ -395,7 +395,7 @@ emd_auction_kernel(Pts xyz1, Pts xyz2, int N, float eps, int iters, int flags, i
     for (int t = 0; t < iters; t++) {
         const bool last = (t == iters - 1);
         // ---- 1. list of unassigned bidders (emd_cuda.cu:23-93), ascending, identical in every CTA -------
-        if (t > 0) {  // prices moved in the previous iteration: refresh the per-tile upper bound of c (same barrier interval)
+        if (t > 0 && (!have_list || (t & 3) == 0)) {  // prices moved in the previous iteration: refresh the per-tile upper bound of c (a stale, higher bound stays valid: with few bidders left only every fourth iteration)
             for (int t0 = wid; t0 < NT; t0 += 4 * EMD_WARPS) {  // four independent tiles per trip
                 // warp maximum with one REDUX on an order-preserving integer image of the float (c may be negative: padding)
                 int b[4];
