@@ -144,20 +144,8 @@ __device__ __forceinline__ float bid_value_exact(float s, float price) {
     return __double2float_rn(__dsub_rn(__dsub_rn(3.0, (double)__fsqrt_rn(s)), (double)price));
 }
 
-// 12-bit Morton cell of a point (4 bits per axis over [0,1]); only the spatial coherence of the internal order
-// depends on it, never a result.
-__device__ __forceinline__ unsigned spread4(unsigned v) {
-    v = (v | (v << 4)) & 0x0C3u;
-    v = (v | (v << 2)) & 0x249u;
-    return v;
-}
-__device__ __forceinline__ unsigned morton12(float3 p) {
-    const unsigned qx = (unsigned)min(max((int)(p.x * 16.f), 0), 15), qy = (unsigned)min(max((int)(p.y * 16.f), 0), 15),
-                   qz = (unsigned)min(max((int)(p.z * 16.f), 0), 15);
-    return spread4(qx) | (spread4(qy) << 1) | (spread4(qz) << 2);
-}
-constexpr int EMD_CELLS = 4096;
-// 18-bit Morton key (6 bits per axis); its top 12 bits are the cell above, so ordering by (cell, key) == ordering by key
+// 18-bit Morton key (6 bits per axis over [0,1]); only the spatial coherence of the internal order depends on it, never a
+// result.  Any prefix of it is a valid cell number: ordering by (cell, key) == ordering by key
 __device__ __forceinline__ unsigned spread6(unsigned v) {
     v = (v | (v << 8)) & 0x0000300Fu;
     v = (v | (v << 4)) & 0x000030C3u;
@@ -299,19 +287,26 @@ emd_auction_kernel(Pts xyz1, Pts xyz2, int N, float eps, int iters, int flags, i
         // Counting sort by Morton cell (histogram with shared-memory atomics, block scan, scatter, in-cell ranking).
         // Every tie rule uses original indices, so results never depend on the internal order (the parity tests run it
         // sorted, in natural order and with N > 4096); it only has to be the SAME order in all CTAs of a cluster.
-        int *hist = reinterpret_cast<int *>(S.pub);     // 16 KB of scratch (pub holds 16 N >= 16 KB for N >= 1024)
-        unsigned short *rnk = S.unass;                  // rank of every point inside its cell
+        // Scratch: the cold arrays (bids, assignment, per-object maxima, seeds: 38 B/point) are not in use yet.  The more
+        // cells, the cheaper the quadratic in-cell ranking for clustered clouds: cells = 8 N rounded down to a power of two,
+        // 4096..16384 (a prefix of the 18-bit key, so that ordering by (cell, key) == ordering by key).
+        int cbits = 12;
+        while (cbits < 14 && (1 << (cbits + 1)) <= 8 * N) cbits++;
+        const int ncell = 1 << cbits, cshift = 18 - cbits;
+        int *hist = reinterpret_cast<int *>(S.pub);                              // ncell ints, one pad word per 32: cell c lives at H(c)
+        unsigned *tmp = reinterpret_cast<unsigned *>(hist + ncell + ncell / 32); // N keys
+        unsigned short *rnk = reinterpret_cast<unsigned short *>(S.pbest);       // N arrival ranks inside the cell (partials buffer: >= 8 KB)
+        auto H = [](int c) -> int { return c + (c >> 5); };  // a thread scans 8..32 consecutive cells: the pad keeps the lanes on different banks
         for (int pass = 0; pass < 2; pass++) {  // 0: targets, 1: predictions
             const Pts &src = pass ? xyz1 : xyz2;
-            for (int c = tid; c < EMD_CELLS; c += T) hist[c] = 0;
+            for (int c = tid; c < ncell + ncell / 32; c += T) hist[c] = 0;
             __syncthreads();
-            for (int k = tid; k < N; k += T) rnk[k] = (unsigned short)atomicAdd(&hist[morton12(ld_xyz(src, cloud, k))], 1);
+            for (int k = tid; k < N; k += T) rnk[k] = (unsigned short)atomicAdd(&hist[H((int)(morton18(ld_xyz(src, cloud, k)) >> cshift))], 1);
             __syncthreads();
-            {   // exclusive prefix sum over the cells: 8 consecutive cells per thread + block scan
-                constexpr int CPT = EMD_CELLS / EMD_THREADS;
-                int v[CPT], sum = 0;
-#pragma unroll
-                for (int i = 0; i < CPT; i++) { v[i] = hist[tid * CPT + i]; sum += v[i]; }
+            {   // exclusive prefix sum over the cells: ncell / T consecutive cells per thread + block scan
+                const int cpt = ncell / EMD_THREADS;
+                int sum = 0;
+                for (int i = 0; i < cpt; i++) sum += hist[H(tid * cpt + i)];
                 int incl2 = sum;
 #pragma unroll
                 for (int o = 1; o < 32; o <<= 1) {
@@ -322,24 +317,24 @@ emd_auction_kernel(Pts xyz1, Pts xyz2, int N, float eps, int iters, int flags, i
                 __syncthreads();
                 int base = incl2 - sum;
                 for (int w = 0; w < wid; w++) base += S.wsum[w];
-#pragma unroll
-                for (int i = 0; i < CPT; i++) { hist[tid * CPT + i] = base; base += v[i]; }
+                for (int i = 0; i < cpt; i++) { const int v = hist[H(tid * cpt + i)]; hist[H(tid * cpt + i)] = base; base += v; }
             }
             __syncthreads();
             // scatter (fine key | original index) in arrival order, then rank every point among its cell mates by that
             // unique key: the final internal order is the full Morton order, a deterministic function of the input and
             // hence identical in every CTA of the cluster (the replicas exchange internal indices)
-            unsigned *tmp = S.last;
             for (int k = tid; k < N; k += T) {
                 const float3 p = ld_xyz(src, cloud, k);
-                tmp[hist[morton12(p)] + (int)rnk[k]] = (morton18(p) << 12) | (unsigned)k;
+                const unsigned k18 = morton18(p);
+                tmp[hist[H((int)(k18 >> cshift))] + (int)rnk[k]] = (k18 << 12) | (unsigned)k;
             }
             __syncthreads();
             for (int k = tid; k < N; k += T) {
                 const float3 p = ld_xyz(src, cloud, k);
-                const int cell = (int)morton12(p);
-                const unsigned key = (morton18(p) << 12) | (unsigned)k;
-                const int lo = hist[cell], hi = (cell + 1 < EMD_CELLS) ? hist[cell + 1] : N;
+                const unsigned k18 = morton18(p);
+                const int cell = (int)(k18 >> cshift);
+                const unsigned key = (k18 << 12) | (unsigned)k;
+                const int lo = hist[H(cell)], hi = (cell + 1 < ncell) ? hist[H(cell + 1)] : N;
                 int pos = lo;
                 for (int q = lo; q < hi; q++) pos += (tmp[q] < key) ? 1 : 0;
                 if (pass == 0) { S.tperm[pos] = (unsigned short)k; S.tgt[pos] = make_float4(p.x, p.y, p.z, 3.0f); }
