@@ -34,7 +34,7 @@ WORKLOAD = ("config2: Chamfer+EMD fwd+bwd, B=32 per GPU, N=M=2048, Table-shaped 
             "regimes independent/noisy alternating, eps=0.005, iters=50")
 FLOP_PER_EMD_EVAL = 11   # 8 (distance) + sqrt + 2 adds
 FLOP_PER_CHAMFER_EVAL = 8
-NCU_AUCTION_DRAM_BYTES = 1660416  # ncu --set full, one launch (profiles/r1_s2_emd_auction_full.txt)
+NCU_AUCTION_DRAM_BYTES = 1670656  # ncu --set full, one launch (profiles/r1_s2_emd_auction_full.txt)
 
 
 def peaks():
