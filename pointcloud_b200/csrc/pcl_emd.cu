@@ -5,8 +5,8 @@
 // persistent kernel.  A cloud is owned by a thread-block cluster of CS CTAs (CS in {1,2,4,8,16}, chosen so
 // that B*CS fills the 148 SMs).  Every CTA keeps the whole auction state of its cloud in shared memory
 // (targets, prices, assignment, inverse assignment) as a REPLICA:
-//   0. set-up: both clouds are put into an internal Morton order (counting sort), targets are cut into tiles of
-//      32 with a bounding box; every tie rule is evaluated on ORIGINAL indices, so the order never changes a result;
+//   0. set-up: both clouds are put into an internal Morton order (counting sort over up to 16384 cells + in-cell ranking),
+//      targets are cut into tiles of 32 with a bounding box; every tie rule is evaluated on ORIGINAL indices, so the order never changes a result;
 //   1. every CTA compacts the list of unassigned bidders from its replica (identical in all CTAs);
 //   2. the bidders are dealt to the CTAs of the cluster and scanned through a dynamic work queue, either with one
 //      lane per bidder (a warp = 32 neighbouring bidders x a slice of tiles, broadcast LDS.128, whole tiles skipped
@@ -28,6 +28,10 @@
 // the same inequality on bounds (distance to the tile's box, tile maximum of c).  Skipped candidates are strictly
 // below the final second best, so best / second-best / argmax are exactly the reference's (derivation in DESIGN.md
 // "Why skipping is exact").
+// Per-iteration fixed costs are kept short because late iterations have only a handful of bidders: the tile maxima are
+// refreshed with one REDUX per tile, decide + commit of the resolve phase is one pass, many filter survivors of a
+// warp-per-bidder step are reduced to their top two with warp reductions, the first work item of a warp needs no atomic,
+// and with at most 32 bidders left warp 0 writes the next list of unassigned bidders while it commits the bids.
 // The reference's GetMax race (last writer wins inside a +-1e-6 window) is resolved as
 // "largest bidder index wins" (atomicMax), identical to oracle/emd_oracle.c.
 // Clouds of 4097..8192 points keep the hot half of the state (targets, prices) in shared memory and the cold half
