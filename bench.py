@@ -208,7 +208,10 @@ def run_reference(args):
     if rank != 0:
         return
     sample = 16
-    steps, warm = max(1, min(args.steps, 10)), max(1, min(args.warmup, 2))
+    # K steps as asked, unless that would take more than about two minutes on this host (one step of the sample is ~0.2 s on
+    # 16 cores): then as many as fit; the line reports the number actually timed
+    t1 = max(cpu_baseline(sample, 1, 1)["ms_per_step"] * 1e-3, 1e-3)
+    steps, warm = max(1, min(args.steps, int(120.0 / t1))), max(1, min(args.warmup, 2))
     cb = cpu_baseline(sample, steps, warm)
     line = {"metric": METRIC, "value": cb["value"], "unit": UNIT, "n_gpus": args.gpus, "steps": steps, "warmup": warm,
             "ms_per_step": cb["ms_per_step"], "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32",
@@ -454,7 +457,7 @@ def main():
         except Exception as ex:  # the reference build is optional context
             reference_gpu = {"unavailable": repr(ex)}
         if world == 1 and not args.no_cpu_baseline:
-            cb = cpu_baseline(8, 3, 1)
+            cb = cpu_baseline(16, 40, 2)  # ~10 s of CPU work on 16 cores
             cb = {k: cb[k] for k in ("value", "unit", "cores", "kind", "sample")}
 
     if rank == 0:
