@@ -181,6 +181,16 @@ PCL_API int pcl_emd_feat_mse_bwd(const void *feat, int dtype1, int64_t bs1, int6
                          const int32_t *assignment, int B, int N, int F,
                          const float *grad_sums, float *grad_feat, void *stream);
 
+/*
+ * Per-cloud class filter of a labelled target for FilteringChamferDistance (utils.py:110-124,222-226):
+ * for every cloud the rows whose label -- target[..., label_channel] truncated to an integer, as `.long()` -- is one of
+ * `labels` (a HOST array of n_labels <= 16 values) are copied, in order, to the front of out_xyz[b] ((B,N,3) fp32, the rest
+ * zero-filled like F.pad) and lengths[b] (int64, device) receives their number: the (points, y_lengths) pair
+ * chamfer_distance takes, without the reference's per-cloud Python loop and without a host synchronisation.
+ */
+PCL_API int pcl_class_filter(const void *target, int dtype, int64_t bs, int64_t rs, int B, int N, int label_channel,
+                     const int64_t *labels, int n_labels, float *out_xyz, int64_t *lengths, void *stream);
+
 /* ------------------------------------------------------------------ sampling ------ */
 /*
  * Farthest point sampling: replaces pointnet2_ops._ext.furthest_point_sampling (models/pointnet2_utils.py:6,89-90)

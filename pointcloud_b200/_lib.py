@@ -39,6 +39,7 @@ _SIGNATURES = {
     "pcl_emd_seg_ce_bwd": (c_int, _PTS + [c_void_p, c_void_p, c_int, c_int, c_int, c_void_p, c_void_p, c_void_p]),
     "pcl_emd_feat_mse_fwd": (c_int, _PTS + _PTS + [c_void_p, c_int, c_int, c_int, c_void_p, c_void_p, c_size_t, c_void_p]),
     "pcl_emd_feat_mse_bwd": (c_int, _PTS + _PTS + [c_void_p, c_int, c_int, c_int, c_void_p, c_void_p, c_void_p]),
+    "pcl_class_filter": (c_int, _PTS + [c_int, c_int, c_int, c_void_p, c_int, c_void_p, c_void_p, c_void_p]),
     "pcl_fps_max_points": (c_int, []),
     "pcl_fps": (c_int, _PTS + [c_int, c_int, c_int, c_void_p, c_int, c_void_p, c_void_p]),
     "pcl_ball_query": (c_int, _PTS + _PTS + [c_int, c_int, c_int, c_float, c_int, c_void_p, c_void_p]),

@@ -122,6 +122,48 @@ feat_mse_bwd_kernel(Pts feat, Pts tfeat, const int *__restrict__ assignment, int
     }
 }
 
+// Per-cloud class filter of the target + left-packed copy of the kept xyz (stable order), zero padding and the number of
+// kept points -- FilteringChamferDistance's per-cloud Python loop (utils.py:110-124,222-226) as one launch without a host
+// synchronisation.  One CTA per cloud; a running offset carries the block-wide prefix from chunk to chunk.
+constexpr int CF_THREADS = 256, CF_MAX_LABELS = 16;
+struct LabelSet { int n; long long v[CF_MAX_LABELS]; };
+
+__global__ void __launch_bounds__(CF_THREADS)
+class_filter_kernel(Pts target, int N, int label_channel, LabelSet labels, float *__restrict__ out_xyz, long long *__restrict__ lengths) {
+    __shared__ int wsum[CF_THREADS / 32];
+    __shared__ int base_s;
+    const int b = blockIdx.x, tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
+    if (tid == 0) base_s = 0;
+    __syncthreads();
+    float *out = out_xyz + (size_t)b * N * 3;
+    for (int i0 = 0; i0 < N; i0 += CF_THREADS) {
+        const int i = i0 + tid;
+        bool keep = false;
+        float3 p = make_float3(0.f, 0.f, 0.f);
+        if (i < N) {
+            const int64_t o = (int64_t)b * target.bs + (int64_t)i * target.rs;
+            const long long lab = (long long)ld_any(target, o + label_channel);  // .long(): truncation (utils.py:119)
+            for (int k = 0; k < labels.n; k++) keep = keep || (lab == labels.v[k]);
+            if (keep) p = make_float3(ld_any(target, o), ld_any(target, o + 1), ld_any(target, o + 2));
+        }
+        const unsigned m = __ballot_sync(0xffffffffu, keep);
+        if (lane == 0) wsum[wid] = __popc(m);
+        __syncthreads();
+        int off = base_s, tot = 0;
+        for (int w = 0; w < CF_THREADS / 32; w++) { const int v = wsum[w]; off += (w < wid) ? v : 0; tot += v; }
+        if (keep) {
+            const int pos = off + __popc(m & ((1u << lane) - 1u));
+            out[pos * 3 + 0] = p.x; out[pos * 3 + 1] = p.y; out[pos * 3 + 2] = p.z;
+        }
+        __syncthreads();
+        if (tid == 0) base_s += tot;
+    }
+    __syncthreads();
+    const int len = base_s;
+    for (int e = len * 3 + tid; e < N * 3; e += CF_THREADS) out[e] = 0.f;  // F.pad zeros (utils.py:226)
+    if (tid == 0) lengths[b] = len;
+}
+
 int ep_blocks(size_t total) {
     const size_t b = (total + EP_THREADS - 1) / EP_THREADS;
     return (int)(b < 1 ? 1 : (b > 4 * 148 ? 4 * 148 : b));
@@ -191,6 +233,22 @@ extern "C" int pcl_emd_feat_mse_bwd(const void *feat, int dtype1, int64_t bs1, i
     if (!feat || !tfeat || !assignment || !grad_sums || !grad_feat) { set_error("emd_feat_mse_bwd: null argument"); return PCL_E_ARG; }
     const Pts a{feat, bs1, rs1, dtype1}, t{tfeat, bs2, rs2, dtype2};
     feat_mse_bwd_kernel<<<ep_blocks((size_t)B * N), EP_THREADS, 0, (cudaStream_t)stream>>>(a, t, assignment, B, N, F, grad_sums, grad_feat);
+    PCL_CUDA(cudaGetLastError());
+    return PCL_OK;
+}
+
+extern "C" int pcl_class_filter(const void *target, int dtype, int64_t bs, int64_t rs, int B, int N, int label_channel,
+                                const int64_t *labels /* host */, int n_labels, float *out_xyz, int64_t *lengths, void *stream) {
+    if (B < 0 || N < 1 || label_channel < 0) { set_error("class_filter: bad size B=%d N=%d channel=%d", B, N, label_channel); return PCL_E_SHAPE; }
+    if (n_labels < 0 || n_labels > CF_MAX_LABELS || (n_labels > 0 && !labels)) { set_error("class_filter: 0..%d labels", CF_MAX_LABELS); return PCL_E_ARG; }
+    if (!dtype_ok(dtype)) { set_error("class_filter: bad dtype"); return PCL_E_ARG; }
+    if (B == 0) return PCL_OK;
+    if (!target || !out_xyz || !lengths) { set_error("class_filter: null argument"); return PCL_E_ARG; }
+    LabelSet ls;
+    ls.n = n_labels;
+    for (int k = 0; k < CF_MAX_LABELS; k++) ls.v[k] = (k < n_labels) ? (long long)labels[k] : 0;
+    const Pts t{target, bs, rs, dtype};
+    class_filter_kernel<<<B, CF_THREADS, 0, (cudaStream_t)stream>>>(t, N, label_channel, ls, out_xyz, (long long *)lengths);
     PCL_CUDA(cudaGetLastError());
     return PCL_OK;
 }

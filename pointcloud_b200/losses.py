@@ -50,6 +50,21 @@ class FilteringChamferDistance:
 
     def _filter_pad(self, target, dtype):
         f = self.filter
+        if (isinstance(f, FilterClasses) and target.dim() == 3 and target.is_cuda and dtype == torch.float32
+                and target.dtype in (torch.float32, torch.float16, torch.bfloat16) and target.stride(2) == 1
+                and 0 < len(f.whitelist) <= 16 and target.shape[1] > 0):
+            # one launch, no host synchronisation: kept points packed to the front of a (B, N, 3) buffer + their counts
+            import ctypes
+            L = _lib.lib()
+            b, n, _ = target.shape
+            with torch.cuda.device(target.device):
+                xyz = torch.empty(b, n, 3, device=target.device, dtype=torch.float32)
+                num_points = torch.empty(b, device=target.device, dtype=torch.int64)
+                labels = (ctypes.c_int64 * len(f.whitelist))(*[int(v) for v in f.whitelist])
+                rc = L.pcl_class_filter(*_lib.pts_args(target), b, n, int(f.label_dim), labels, len(f.whitelist),
+                                        xyz.data_ptr(), num_points.data_ptr(), _lib.stream_ptr())
+                _lib.check(rc, "pcl_class_filter")
+            return xyz, num_points
         if isinstance(f, FilterClasses) and target.dim() == 3:
             label = target[:, :, f.label_dim].long()                                   # (B, N)
             mask = reduce(torch.logical_or, [label == v for v in f.whitelist])         # (B, N)

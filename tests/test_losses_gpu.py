@@ -261,3 +261,34 @@ def test_fused_feature_term_entry_points():
     ref.backward()
     assert float(s2[0] / s2[1]) == pytest.approx(float(ref), rel=REL) and float(s2[1]) == b * n * 3
     np.testing.assert_allclose(npy(predf.grad), npy(q.grad), rtol=REL, atol=1e-10)
+
+
+def test_class_filter_kernel_matches_the_reference_loop():
+    """pcl_class_filter (through FilteringChamferDistance._filter_pad) against the reference's per-cloud loop
+    (utils.py:110-124,222-226): kept points in order, zero padding, counts; several labels; fp16 target; a cloud without the class."""
+    from pointcloud_b200.losses import FilterClasses, FilteringChamferDistance
+    g = torch.Generator().manual_seed(41)
+    b, n = 5, 1000
+    target = torch.rand(b, n, 4, generator=g)
+    target[:, :, 3] = torch.randint(0, 5, (b, n), generator=g).float()
+    target[2, :, 3] = 4.0                                   # cloud 2 holds only class 4
+    for whitelist, dt in (([1], torch.float32), ([0, 3], torch.float32), ([2], torch.float16)):
+        t = target.to(dt).cuda()
+        fcd = FilteringChamferDistance(FilterClasses(whitelist, label_dim=3))
+        xyz, num = fcd._filter_pad(t, torch.float32)
+        assert xyz.shape == (b, n, 3) and num.dtype == torch.int64
+        for i in range(b):
+            lab = t[i, :, 3].long()
+            mask = torch.zeros(n, dtype=torch.bool, device="cuda")
+            for v in whitelist:
+                mask |= lab == v
+            ref = t[i][mask][:, :3].float()
+            k = int(num[i])
+            assert k == ref.shape[0]
+            assert torch.equal(xyz[i, :k], ref) and not xyz[i, k:].any()
+    # the loss through the kernel equals the loss through the reference-structure loop (any other callable falls back to it)
+    pred = torch.rand(b, 37, 3, generator=g).cuda().requires_grad_()
+    tc = target.cuda()
+    l1 = FilteringChamferDistance(FilterClasses([1], label_dim=3))(pred, tc)
+    l2 = FilteringChamferDistance(lambda p: FilterClasses([1], label_dim=3)(p))(pred, tc)
+    assert float(l1) == pytest.approx(float(l2), rel=REL)
