@@ -1,7 +1,7 @@
 """CPU oracles for the reconstruction-loss hot path.  TEST INFRASTRUCTURE ONLY.
 
 Only tests/, __graft_entry__.smoke() and bench.py's cpu_baseline / --impl reference legs may
-import this package; pointcloud_b200/ never does (tests/test_layout.py enforces it).
+import this package; pointcloud_b200/ never does (tests/test_abi_cpu.py::test_product_package_never_touches_the_oracle enforces it).
 
   * emd_forward / emd_backward   -> oracle/emd_oracle.c   (reference: loss/emd/emd_cuda.cu)
   * chamfer_forward / _backward  -> oracle/chamfer_oracle.c (pytorch3d 0.7.2, PARITY UNPINNED)

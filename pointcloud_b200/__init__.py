@@ -9,13 +9,13 @@ from . import cfg
 from .chamfer import chamfer_distance, chamfer_forward_raw
 from .emd_module import emdFunction, emdModule, emd_forward_raw
 from .losses import (ChamferDistance, EarthMoverDistance, FilterClasses, FilteringChamferDistance,
-                     SegmentingChamferDistance, StatePredictionLoss)
+                     SegmentingChamferDistance)
 from .sampling import farthest_point_sample, query_ball_point, sample_farthest_points
 from .sharded import ShardedLoss, shard_bounds
 
 __all__ = [
     "cfg", "chamfer_distance", "chamfer_forward_raw", "emdFunction", "emdModule", "emd_forward_raw",
     "ChamferDistance", "FilteringChamferDistance", "SegmentingChamferDistance", "EarthMoverDistance",
-    "StatePredictionLoss", "FilterClasses", "ShardedLoss", "shard_bounds",
+    "FilterClasses", "ShardedLoss", "shard_bounds",
     "farthest_point_sample", "sample_farthest_points", "query_ball_point",
 ]

@@ -5,11 +5,12 @@
 // index on exact ties, variable lengths, point-mean + batch-mean; backward scatters
 // 2*g*(p - q[idx]) to both clouds.
 //
-// Forward kernel (D == 3): one CTA = 128 threads x QPT register-resident queries of one cloud and one
-// direction; the target cloud streams through shared memory in float4 {x,y,z,0} tiles (one
-// broadcast LDS.128 feeds QPT distance evaluations per thread); distance arithmetic is written with
-// explicit __fmul_rn/__fadd_rn/__fmaf_rn so that the compiler cannot re-associate or contract it
-// differently from the oracle (bit-exact distances => bit-exact argmin).
+// Forward kernel (D == 3): one CTA = 128 threads x QPT register-resident queries of one cloud and one direction; the
+// target cloud streams through shared memory in tiles stored per PAIR of targets ({x0,x1,y0,y1}, {z0,z1,|t0|^2,|t1|^2}:
+// the operand layout of FFMA2).  The scan evaluates an APPROXIMATE expanded-form distance with packed FFMA2 and only
+// remembers which 32-target chunks can hold the nearest neighbour; those chunks are re-scanned with the oracle's
+// arithmetic (explicit __fsub_rn/__fmul_rn/__fadd_rn/__fmaf_rn), which alone decides distance, index and the
+// lowest-index tie rule (derivation above chamfer_nn3_kernel and in DESIGN.md 3.2).
 #include <stdlib.h>
 
 #include "pcl_common.cuh"
@@ -51,6 +52,13 @@ __device__ __forceinline__ float lo2(u64 v) { return __uint_as_float((unsigned)v
 __device__ __forceinline__ float hi2(u64 v) { return __uint_as_float((unsigned)(v >> 32)); }
 __device__ __forceinline__ u64 ffma2(u64 a, u64 b, u64 c) { u64 r; asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(r) : "l"(a), "l"(b), "l"(c)); return r; }
 __device__ __forceinline__ float fmin3(float a, float b, float c) { float r; asm("min.f32 %0, %1, %2, %3;" : "=f"(r) : "f"(a), "f"(b), "f"(c)); return r; }  // NaN operands are ignored
+
+// length of cloud n, clamped to [0, P]: pytorch3d raises on lengths > P; a kernel cannot, but it must not read past the cloud
+__device__ __forceinline__ int len_of(const int64_t *len, int n, int P) {
+    if (!len) return P;
+    const int64_t v = len[n];
+    return (int)(v < 0 ? 0 : (v > P ? P : v));
+}
 
 template <bool FMA>
 __device__ __forceinline__ float sqdist3(float qx, float qy, float qz, const float4 &t) {
@@ -139,8 +147,8 @@ chamfer_nn3_kernel(Pts x, const int64_t *__restrict__ x_len, Pts y, const int64_
     const int PQ = dir ? P2 : P1;
     const int q0 = blockIdx.x * C3_QUERIES;
     if (q0 >= PQ) return;  // block-uniform
-    const int lq = dir ? (y_len ? (int)y_len[n] : P2) : (x_len ? (int)x_len[n] : P1);
-    const int lt = dir ? (x_len ? (int)x_len[n] : P1) : (y_len ? (int)y_len[n] : P2);
+    const int lq = dir ? len_of(y_len, n, P2) : len_of(x_len, n, P1);
+    const int lt = dir ? len_of(x_len, n, P1) : len_of(y_len, n, P2);
     float *dist = (dir ? dist_y : dist_x) + (size_t)n * PQ;
     int *idx = (dir ? idx_y : idx_x) + (size_t)n * PQ;
     const float INF = __int_as_float(0x7f800000);
@@ -311,8 +319,8 @@ chamfer_nnD_kernel(Pts x, const int64_t *__restrict__ x_len, Pts y, const int64_
     const int PQ = dir ? P2 : P1;
     const int q0 = blockIdx.x * CH_THREADS;
     if (q0 >= PQ) return;
-    const int lq = dir ? (y_len ? (int)y_len[n] : P2) : (x_len ? (int)x_len[n] : P1);
-    const int lt = dir ? (x_len ? (int)x_len[n] : P1) : (y_len ? (int)y_len[n] : P2);
+    const int lq = dir ? len_of(y_len, n, P2) : len_of(x_len, n, P1);
+    const int lt = dir ? len_of(x_len, n, P1) : len_of(y_len, n, P2);
     float *dist = (dir ? dist_y : dist_x) + (size_t)n * PQ;
     int *idx = (dir ? idx_y : idx_x) + (size_t)n * PQ;
     const int i = q0 + threadIdx.x;
@@ -364,7 +372,7 @@ __global__ void chamfer_finish_kernel(const float *__restrict__ partial, int B, 
         const int used = dir ? nby : nbx;
         double s = 0.0;
         for (int k = 0; k < used; k++) s += (double)partial[((size_t)dir * B + n) * nblk + k];
-        const int64_t len = dir ? (y_len ? y_len[n] : P2) : (x_len ? x_len[n] : P1);
+        const int64_t len = dir ? len_of(y_len, n, P2) : len_of(x_len, n, P1);
         a += s / (double)(len > 1 ? len : 1);
     }
     acc[dir][lane] = a;
@@ -386,8 +394,8 @@ chamfer_bwd_kernel(Pts x, const int64_t *__restrict__ x_len, Pts y, const int64_
     const int i = blockIdx.x * blockDim.x + threadIdx.x;
     const Pts q = dir ? y : x, t = dir ? x : y;
     const int PQ = dir ? P2 : P1, PT = dir ? P1 : P2;
-    const int lq = dir ? (y_len ? (int)y_len[n] : P2) : (x_len ? (int)x_len[n] : P1);
-    const int lt = dir ? (x_len ? (int)x_len[n] : P1) : (y_len ? (int)y_len[n] : P2);
+    const int lq = dir ? len_of(y_len, n, P2) : len_of(x_len, n, P1);
+    const int lt = dir ? len_of(x_len, n, P1) : len_of(y_len, n, P2);
     if (i >= lq || lt <= 0) return;
     const float g = __ldg(grad_out + dir);
     const float gd = g / (float)(B > 1 ? B : 1) / (float)(lq > 1 ? lq : 1);

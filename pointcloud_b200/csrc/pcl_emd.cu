@@ -34,8 +34,8 @@
 // and with at most 32 bidders left warp 0 writes the next list of unassigned bidders while it commits the bids.
 // The reference's GetMax race (last writer wins inside a +-1e-6 window) is resolved as
 // "largest bidder index wins" (atomicMax), identical to oracle/emd_oracle.c.
-// Clouds of 4097..8192 points keep the hot half of the state (targets, prices) in shared memory and the cold half
-// (bids, per-object maxima, assignment arrays) in a per-CTA global-memory region.
+// Clouds of 3585..8192 points (EMD_SMEM_ONLY_N < N <= EMD_MAX_N) keep the hot half of the state (targets, prices) in
+// shared memory and the cold half (bids, per-object maxima, assignment arrays) in a per-CTA global-memory region.
 #include <cooperative_groups.h>
 #include <stdlib.h>
 
@@ -59,7 +59,7 @@ namespace {
 #endif
 constexpr int EMD_THREADS = PCL_EMD_THREADS;
 constexpr int EMD_WARPS = EMD_THREADS / 32;
-constexpr int EMD_MAX_N = 8192;      // 4097..8192: the cold half of the state lives in a per-CTA global-memory region (L2)
+constexpr int EMD_MAX_N = 8192;      // EMD_SMEM_ONLY_N+1..8192: the cold half of the state lives in a per-CTA global-memory region (L2)
 constexpr int EMD_SMEM_ONLY_N = 3584;  // up to here the whole auction state (58 B/point + 9 KB) fits into 227 KB of shared memory
 constexpr int TILE = 32;  // targets per spatial tile (one bounding box per tile)
 constexpr int EMD_WPB_MAX = 6 * EMD_WARPS;  // at most this many bidders per CTA: warp-per-bidder scan (swept on config 2: 48..128)
@@ -948,9 +948,29 @@ emd_weighted_bwd_kernel(Pts xyz1, Pts xyz2, int N, const int *__restrict__ assig
     grad[o * 3 + 0] = r.x; grad[o * 3 + 1] = r.y; grad[o * 3 + 2] = r.z;
 }
 
-int pick_cluster(int B, int N, int sm_count, size_t smem, cudaStream_t st) {
+// cluster size wanted for B clouds on sm_count SMs: the largest power of two <= 16 with B * cs <= sm_count
+int cluster_size_for(int B, int sm_count) {
     int cs = 16;
     while (cs > 1 && (long)B * cs > sm_count) cs >>= 1;
+    return cs;
+}
+// SM count of the current device; 148 (B200) when no device can be queried (size queries on a CPU-only host)
+int sm_count_or_default() {
+    DeviceInfo di;
+    if (device_info(&di) != PCL_OK) return 148;
+    return di.sm_count;
+}
+
+int pick_cluster(int B, int N, int sm_count, size_t smem, cudaStream_t st) {
+    // the occupancy query costs a few microseconds of host time: remembered per (device, B, shared-memory size)
+    struct Memo { int dev, B; size_t smem; int cs; };
+    static thread_local Memo memo[8];
+    static thread_local int memo_n = 0;
+    int dev = 0;
+    if (cudaGetDevice(&dev) != cudaSuccess) { (void)cudaGetLastError(); dev = -1; }
+    for (int i = 0; i < memo_n; i++)
+        if (memo[i].dev == dev && memo[i].B == B && memo[i].smem == smem) return memo[i].cs;
+    int cs = cluster_size_for(B, sm_count);
     while (cs > 1) {  // is a cluster of this size schedulable with this much shared memory?
         cudaLaunchConfig_t cfg = {};
         cfg.gridDim = dim3(B * cs); cfg.blockDim = dim3(EMD_THREADS); cfg.dynamicSmemBytes = smem; cfg.stream = st;
@@ -965,7 +985,24 @@ int pick_cluster(int B, int N, int sm_count, size_t smem, cudaStream_t st) {
         cs >>= 1;
     }
     (void)N;
+    memo[memo_n < 8 ? memo_n++ : (memo_n = 8, 7)] = Memo{dev, B, smem, cs};
     return cs;
+}
+
+// development aids, read once per process: PCL_EMD_NO_SORT, PCL_EMD_PCAP, PCL_EMD_WPB, PCL_EMD_ITEMS, PCL_EMD_PROFILE
+struct EmdEnv { bool no_sort, profile; int pcap, wpb, items; };
+const EmdEnv &emd_env() {
+    static const EmdEnv e = [] {
+        EmdEnv v;
+        v.no_sort = getenv("PCL_EMD_NO_SORT") != nullptr;
+        v.profile = getenv("PCL_EMD_PROFILE") != nullptr;
+        const char *s;
+        v.pcap = (s = getenv("PCL_EMD_PCAP")) ? atoi(s) * 32 : 0;
+        v.wpb = (s = getenv("PCL_EMD_WPB")) ? atoi(s) : -1;
+        v.items = (s = getenv("PCL_EMD_ITEMS")) ? atoi(s) : 0;
+        return v;
+    }();
+    return e;
 }
 
 }  // namespace
@@ -980,8 +1017,7 @@ extern "C" size_t pcl_emd_workspace_bytes(int B, int N) {
     const size_t red = (size_t)RED_BLOCKS * 2 * sizeof(double), prof = ((size_t)(B > 0 ? B : 0) * 16 * 16 + 512) * sizeof(long long);
     size_t cold = 0;
     if (N > EMD_SMEM_ONLY_N && B > 0) {  // large clouds: per-CTA global region for the cold state, sized for the largest cluster
-        int cs = 16;
-        while (cs > 1 && (long)B * cs > 148) cs >>= 1;
+        const int cs = cluster_size_for(B, sm_count_or_default());  // the same rule pick_cluster starts from (it can only go down)
         cold = (size_t)B * cs * ((emd_cold_bytes(N) + 255) / 256 * 256);
     }
     const size_t m = red > prof ? red : prof;
@@ -1017,15 +1053,16 @@ extern "C" int pcl_emd_fwd(const void *xyz1, int dtype1, int64_t bs1, int64_t rs
     }
     if (N >= 1024 && N <= EMD_SMEM_ONLY_N && emd_smem_bytes(N, EMD_F_SORT) <= (size_t)di.max_smem_optin) flags |= EMD_F_SORT;
     if (N <= EMD_SMEM_ONLY_N && emd_smem_bytes(N, flags | EMD_F_X1) <= (size_t)di.max_smem_optin) flags |= EMD_F_X1;
-    if (getenv("PCL_EMD_NO_SORT")) flags &= ~EMD_F_SORT;  // development aid: natural order (no spatial pruning benefit)
+    const EmdEnv &env = emd_env();
+    if (env.no_sort) flags &= ~EMD_F_SORT;  // development aid: natural order (no spatial pruning benefit)
     int pcap = 2 * EMD_THREADS;  // room for 32 work items with partials; fall back to 16 when shared memory is tight
-    if (const char *e = getenv("PCL_EMD_PCAP")) pcap = atoi(e) * 32;  // development aid: work items with partials
+    if (env.pcap > 0) pcap = env.pcap;  // development aid: work items with partials
     while (pcap > EMD_THREADS && emd_smem_bytes(N, flags, pcap) > (size_t)di.max_smem_optin) pcap -= EMD_THREADS;
     const size_t smem = emd_smem_bytes(N, flags, pcap);
     int wpb_max = EMD_WPB_MAX;
-    if (const char *e = getenv("PCL_EMD_WPB")) wpb_max = atoi(e);  // development aid
+    if (env.wpb >= 0) wpb_max = env.wpb;  // development aid
     int items_target = 2 * EMD_WARPS;  // work items per CTA and iteration in the lane-per-bidder mode (dynamic queue; swept 8..128 on config 2)
-    if (const char *e = getenv("PCL_EMD_ITEMS")) items_target = atoi(e);  // development aid
+    if (env.items > 0) items_target = env.items;  // development aid
     if (smem > (size_t)di.max_smem_optin) { set_error("emd_fwd: N=%d needs %zu B shared memory (> %d)", N, smem, di.max_smem_optin); return PCL_E_UNSUPPORTED; }
     static thread_local int attr_dev = -1;
     int dev = 0;
@@ -1046,8 +1083,7 @@ extern "C" int pcl_emd_fwd(const void *xyz1, int dtype1, int64_t bs1, int64_t rs
     cfg.attrs = at; cfg.numAttrs = 1;
     const Pts p1{xyz1, bs1, rs1, dtype1}, p2{xyz2, bs2, rs2, dtype2};
     // development aid: PCL_EMD_PROFILE=1 makes the workspace receive per-phase clock totals (B*cs*16 int64)
-    static const bool profile = getenv("PCL_EMD_PROFILE") != nullptr;
-    if (profile && !(flags & EMD_F_COLD) && workspace && workspace_bytes >= ((size_t)B * cs * 16 + 512) * sizeof(long long)) {
+    if (env.profile && !(flags & EMD_F_COLD) && workspace && workspace_bytes >= ((size_t)B * cs * 16 + 512) * sizeof(long long)) {
         PCL_CUDA(cudaLaunchKernelEx(&cfg, emd_auction_kernel<true>, p1, p2, N, eps, iters, flags, pcap, wpb_max, items_target, dist, (int *)assignment, (int *)stats, (long long *)workspace, (unsigned char *)nullptr));
     } else {
         PCL_CUDA(cudaLaunchKernelEx(&cfg, emd_auction_kernel<false>, p1, p2, N, eps, iters, flags, pcap, wpb_max, items_target, dist, (int *)assignment, (int *)stats, (long long *)nullptr, (unsigned char *)((flags & EMD_F_COLD) ? workspace : nullptr)));

@@ -164,9 +164,11 @@ class_filter_kernel(Pts target, int N, int label_channel, LabelSet labels, float
     if (tid == 0) lengths[b] = len;
 }
 
-int ep_blocks(size_t total) {
+int ep_blocks(size_t total) {  // grid-stride kernels: at most four CTAs per SM of the current device
+    DeviceInfo di;
+    const size_t cap = 4 * (size_t)(device_info(&di) == PCL_OK ? di.sm_count : 148);
     const size_t b = (total + EP_THREADS - 1) / EP_THREADS;
-    return (int)(b < 1 ? 1 : (b > 4 * 148 ? 4 * 148 : b));
+    return (int)(b < 1 ? 1 : (b > cap ? cap : b));
 }
 
 }  // namespace

@@ -52,7 +52,8 @@ class FilteringChamferDistance:
         f = self.filter
         if (isinstance(f, FilterClasses) and target.dim() == 3 and target.is_cuda and dtype == torch.float32
                 and target.dtype in (torch.float32, torch.float16, torch.bfloat16) and target.stride(2) == 1
-                and 0 < len(f.whitelist) <= 16 and target.shape[1] > 0):
+                and 0 < len(f.whitelist) <= 16 and target.shape[1] > 0 and target.shape[2] >= 3
+                and 0 <= int(f.label_dim) < target.shape[2] and not target.requires_grad):
             # one launch, no host synchronisation: kept points packed to the front of a (B, N, 3) buffer + their counts
             import ctypes
             L = _lib.lib()
@@ -233,46 +234,57 @@ class _MatchedFeatureMSESums(Function):
 
 
 class EarthMoverDistance:
-    """utils.py:245-309.  `fused=True` (default) computes the point term with the fused epilogue kernels
-    (matched-label histogram, weighted sqrt-sum, fused backward); `fused=False` follows the reference's
-    torch-op structure line by line on top of emdModule (used by the parity tests -- both must agree).
+    """utils.py:245-309.  The auction runs in one kernel; the loss around it (matched-label histogram, class
+    weights, weighted sqrt-sum, weighted cross entropy / feature MSE and their backward passes) runs in the
+    fused epilogue kernels instead of the reference's ~25 torch ops.
 
-    `reduce_fn` (optional) is the hook of the batch-sharded wrapper: it is called on the class histogram
-    and on every (numerator, denominator) pair so that they can be all-reduced over the ranks; the default
-    keeps single-GPU semantics."""
+    `all_reduce` / `grad_scale` are the hook of the batch-sharded wrapper (sharded.py): `all_reduce` sums a
+    small vector of whole-batch statistics over the ranks -- once for the class histogram (utils.py:274-275)
+    and once for ALL numerators / denominators / the argmax histogram packed into one vector -- i.e. two
+    dependent collectives for the Segmenter loss and one for the Autoencoder loss; `grad_scale` multiplies the
+    gradient (DDP averaging).  The defaults keep single-GPU semantics without any extra op."""
 
-    def __init__(self, eps=0.002, its=10000, num_classes=None, feature_weight=0.1, fused=True):
+    def __init__(self, eps=0.002, its=10000, num_classes=None, feature_weight=0.1):
         self.loss_fn = emdModule()
         self.eps = eps
         self.iterations = its
         self.C = num_classes
         self.feature_weight = feature_weight  # stored but unused, like the reference (utils.py:251,296)
-        self.fused = fused
-        self.reduce_hist = None   # set by ShardedLoss
-        self.reduce_ratio = None  # set by ShardedLoss
+        self.all_reduce = None   # set by ShardedLoss: tensor -> tensor summed over the ranks
+        self.grad_scale = 1.0    # set by ShardedLoss
 
     def log(self, name, value):  # replaced by train.py:161 (`model.loss_fn.log = model.log`)
         pass
 
     # -- helpers shared by both paths ---------------------------------------------------------------
     def _class_weights(self, hist):
-        if self.reduce_hist is not None:
-            hist = self.reduce_hist(hist)
+        if self.all_reduce is not None:
+            hist = self.all_reduce(hist)                              # collective 1 of 2 (Segmenter only)
         distribution = hist / hist.sum()                              # utils.py:274-275
         class_weights = (1 / (distribution + 1e-4)) ** (1 - 0)        # :285
         class_weights = class_weights / class_weights.sum()           # :286
         return distribution, class_weights
 
-    def _ratio(self, num, den):
-        if self.reduce_ratio is not None:
-            return self.reduce_ratio(num, den)
-        return num / den
+    def _ratios(self, pairs, counts=None):
+        """[num / den for (num, den) in pairs] (+ `counts`) over the WHOLE batch.  Single GPU: plain divisions.
+        Sharded: every numerator, denominator and count travels in ONE all-reduced fp64 vector; the value is the
+        global ratio, the gradient flows through the local numerator only (no denominator on this path depends
+        on the prediction) and is multiplied by `grad_scale`."""
+        if self.all_reduce is None:
+            return [n / d for n, d in pairs], counts
+        flat = [x.detach().double() for nd in pairs for x in nd]
+        packed = torch.stack(flat) if counts is None else torch.cat([torch.stack(flat), counts.double()])
+        g = self.all_reduce(packed)
+        out = []
+        for i, (n, _) in enumerate(pairs):
+            gnum, gden = g[2 * i].float(), g[2 * i + 1].float()
+            local = n / gden
+            out.append((gnum / gden).detach() + self.grad_scale * (local - local.detach()))
+        return out, (None if counts is None else g[2 * len(pairs):])
 
     def _kl(self, pred_hist, distribution):
-        if self.reduce_hist is not None:
-            pred_hist = self.reduce_hist(pred_hist)
         pred_distribution = pred_hist / pred_hist.sum()                              # utils.py:280
-        return F.kl_div(F.log_softmax(pred_distribution, dim=0), F.softmax(distribution, dim=0), reduction='batchmean')  # :283
+        return F.kl_div(F.log_softmax(pred_distribution.float(), dim=0), F.softmax(distribution, dim=0), reduction='batchmean')  # :283
 
     # -- the places where the fused path enters the CUDA library (overridden only by CPU host-logic tests)
     def _auction(self, pred, target):
@@ -295,8 +307,6 @@ class EarthMoverDistance:
         return _MatchedFeatureMSESums.apply(_lib.as_points(pred[:, :, 3:]), _lib.as_points(target[:, :, 3:]), assignment)
 
     def __call__(self, pred, target):
-        if not self.fused:
-            return self._call_reference_structure(pred, target)
         if not pred.is_cuda and type(self)._auction is EarthMoverDistance._auction:
             _lib.require_cuda()
             pred, target = pred.cuda(), target.cuda()
@@ -314,65 +324,23 @@ class EarthMoverDistance:
             class_weights = class_weights.float().contiguous()
             # weighted cross entropy == sum_i w_i * nll_i / sum_i w_i  (F.cross_entropy with weight=, utils.py:295)
             ce_sums, pred_hist = self._ce_sums(pred, matched, class_weights)
+            sums = self._point_sums(xyz1, xyz2, dists, assignment, matched, class_weights)
+            (ce_l, point_l), pred_hist = self._ratios([(ce_sums[0], ce_sums[1]), (sums[0], sums[1])], pred_hist)  # collective 2 of 2
             kl_div = self._kl(pred_hist, distribution)
-            ce_l = self._ratio(ce_sums[0], ce_sums[1])
             feature_l = 0.1 * ce_l
             self.log('train_loss/cross_entropy', ce_l)
             self.log('train_loss/kl_divergence', kl_div)
-            sums = self._point_sums(xyz1, xyz2, dists, assignment, matched, class_weights)
         else:  # general feature loss (utils.py:300-301)
+            sums = self._point_sums(xyz1, xyz2, dists, assignment, None, None)
             if pred.shape[2] == 3 or pred.numel() == 0:
                 matched_feat = target[:, :, 3:].take_along_dim(assignment.long().unsqueeze(-1), 1)
                 feature_l = F.mse_loss(pred[:, :, 3:], matched_feat)  # nan, exactly like the reference on empty features
+                (point_l,), _ = self._ratios([(sums[0], sums[1])])
             else:
                 mse_sums = self._mse_sums(pred, target, assignment)
-                feature_l = self._ratio(mse_sums[0], mse_sums[1])
-            sums = self._point_sums(xyz1, xyz2, dists, assignment, None, None)
+                (feature_l, point_l), _ = self._ratios([(mse_sums[0], mse_sums[1]), (sums[0], sums[1])])  # the one collective
 
-        point_l = self._ratio(sums[0], sums[1])  # utils.py:304
+        # point_l: utils.py:304
         self.log('train_loss/EMD', point_l)
         self.log('train_loss/feature', feature_l)
         return point_l + feature_l
-
-    # -- the reference's own structure, op by op (utils.py:253-309) ----------------------------------
-    def _call_reference_structure(self, pred, target):
-        dists, assignment = self.loss_fn(pred[:, :, :3], target[:, :, :3], self.eps, self.iterations)
-        assignment = assignment.long().unsqueeze(-1)
-        target = target.to(dists.device).take_along_dim(assignment, 1)
-        pred = pred.to(dists.device)
-        weights = torch.ones_like(dists)  # (B, N)
-        if self.C is not None:
-            target_classes = target[:, :, 3].long()
-            distribution = torch.bincount(target_classes.view(-1), minlength=self.C)
-            distribution = distribution / distribution.sum()
-            pred_classes = pred[:, :, 3:].argmax(dim=2)
-            pred_distribution = torch.bincount(pred_classes.view(-1), minlength=self.C)
-            pred_distribution = pred_distribution / pred_distribution.sum()
-            kl_div = F.kl_div(F.log_softmax(pred_distribution, dim=0), F.softmax(distribution, dim=0), reduction='batchmean')
-            class_weights = (1 / (distribution + 1e-4)) ** (1 - 0)
-            class_weights = class_weights / class_weights.sum()
-            weights = class_weights[target_classes]
-            ce_l = F.cross_entropy(pred.permute(0, 2, 1)[:, 3:, :].float(), target_classes, weight=class_weights)
-            feature_l = 0.1 * ce_l
-            self.log('train_loss/cross_entropy', ce_l)
-            self.log('train_loss/kl_divergence', kl_div)
-        else:
-            feature_l = F.mse_loss(pred[:, :, 3:], target[:, :, 3:])
-        point_l = (dists.sqrt() * weights).sum() / weights.sum()
-        self.log('train_loss/EMD', point_l)
-        self.log('train_loss/feature', feature_l)
-        return point_l + feature_l
-
-
-class StatePredictionLoss:
-    """utils.py:311-321 (not on the hot path; kept so that `create_model` finds every loss in one module)."""
-
-    def __init__(self, states, transforms):
-        self.state_losses = {s: F.mse_loss for s in states}
-        self.t = transforms
-        for s in states:
-            if s not in self.t:
-                self.t[s] = lambda x: x
-
-    def __call__(self, pred, target):
-        return torch.stack([loss(pred[s], self.t[s](target[s])) for s, loss in self.state_losses.items()]).mean()

@@ -6,8 +6,12 @@ import torch
 from . import _lib
 
 
-def farthest_point_sample(xyz, npoint, start_idx=None, skip_origin=False):
-    """xyz (B, N, 3+) -> sampled point indices (B, npoint), int64 like the reference wrapper (pointnet2_utils.py:89-90)."""
+def farthest_point_sample(xyz, npoint, start_idx=None, skip_origin=True):
+    """xyz (B, N, 3+) -> sampled point indices (B, npoint), int64 like the reference wrapper (pointnet2_utils.py:89-90).
+
+    `skip_origin=True` (default) is the behaviour of the kernel that wrapper calls (pointnet2_ops `furthest_point_sample`
+    never selects a point with x^2+y^2+z^2 <= 1e-3 after the first [3P-memory]); `skip_origin=False` is the plain torch
+    algorithm kept as a comment in pointnet2_utils.py:64-86 and pytorch3d's `sample_farthest_points`."""
     _lib.require_cuda()
     L = _lib.lib()
     xyz = _lib.as_points(xyz)
@@ -31,7 +35,7 @@ def sample_farthest_points(points, lengths=None, K=50, random_start_point=False)
     start = None
     if random_start_point:
         start = torch.randint(0, points.shape[1], (points.shape[0],))
-    idx = farthest_point_sample(points[:, :, :3], K, start_idx=start)
+    idx = farthest_point_sample(points[:, :, :3], K, start_idx=start, skip_origin=False)
     gathered = torch.gather(points.to(idx.device), 1, idx.unsqueeze(-1).expand(-1, -1, points.shape[2]))
     return gathered, idx
 

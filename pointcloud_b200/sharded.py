@@ -20,27 +20,11 @@ from .losses import ChamferDistance, EarthMoverDistance, FilteringChamferDistanc
 
 
 def _all_reduce_sum(t, group):
+    """Sum a small, freshly created tensor over the ranks of `group`, in place (NCCL on GPUs, gloo in the CPU tests);
+    identity on one rank."""
     if dist.is_available() and dist.is_initialized() and dist.get_world_size(group) > 1:
-        t = t.clone()
         dist.all_reduce(t, op=dist.ReduceOp.SUM, group=group)
     return t
-
-
-class _GlobalRatio:
-    """(sum_r num_r) / (sum_r den_r): value is global, gradient flows through the local numerator only
-    (denominators on this path never depend on the prediction)."""
-
-    def __init__(self, group, scale):
-        self.group, self.scale = group, scale
-
-    def __call__(self, num, den):
-        packed = torch.stack([num.detach().float(), den.detach().float()])
-        g = _all_reduce_sum(packed, self.group)
-        gnum, gden = g[0], g[1]
-        local = num / gden                          # d/d num_local of the global ratio
-        value = (gnum / gden).detach()
-        # value of the global ratio, gradient of scale * local
-        return value + self.scale * (local - local.detach())
 
 
 def shard_bounds(batch: int, world: int, rank: int):
@@ -80,19 +64,23 @@ class ShardedLoss:
         scale = float(world) if self.ddp_average else 1.0
         fn = self.loss_fn
         if isinstance(fn, EarthMoverDistance):
-            if not fn.fused:
-                raise ValueError("ShardedLoss needs EarthMoverDistance(fused=True)")
-            fn.reduce_hist = lambda h: _all_reduce_sum(h, self.group)
-            fn.reduce_ratio = _GlobalRatio(self.group, scale)
+            # Autoencoder loss: ONE collective ([mse num, mse den, sum w sqrt(d), sum w]); Segmenter loss: TWO dependent ones
+            # (class histogram, utils.py:274-275, then [ce num, ce den, sum w sqrt(d), sum w, argmax histogram], :280,295,304)
+            fn.all_reduce = (lambda t: _all_reduce_sum(t, self.group)) if world > 1 else None
+            fn.grad_scale = scale if world > 1 else 1.0
             try:
-                return fn(pred, target)
+                loss = fn(pred, target)
             finally:
-                fn.reduce_hist = None
-                fn.reduce_ratio = None
-        # Chamfer family: loss = sum over local clouds / B_global  (batch_reduction="mean")
+                fn.all_reduce, fn.grad_scale = None, 1.0
+            return loss
+        # Chamfer family (batch_reduction="mean"): global loss = sum_r b_r * local_r / sum_r b_r -- ONE collective of
+        # [b_r * local_r, b_r], both formed on the device (no host->device copy, no synchronisation)
         some = next(iter(pred.values())) if isinstance(pred, dict) else pred
-        b_local = torch.tensor([float(some.shape[0])], device=some.device)
-        b_global = _all_reduce_sum(b_local, self.group)[0]
-        local = fn(pred, target) * (b_local[0] / b_global)     # local mean -> share of the global mean
-        value = _all_reduce_sum(local.detach().reshape(1), self.group)[0]
-        return value + scale * (local - local.detach())
+        b_local = float(some.shape[0])
+        local = fn(pred, target)
+        if world == 1:
+            return local
+        ld = local.detach().double()
+        g = _all_reduce_sum(torch.stack([ld * b_local, torch.full_like(ld, b_local)]), self.group)
+        share = local * (b_local / g[1].float())                 # this rank's share of the global mean
+        return (g[0] / g[1]).float() + scale * (share - share.detach())

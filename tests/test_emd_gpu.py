@@ -86,11 +86,79 @@ def test_emd_matches_unmodified_reference_extension(ref_ext):
             if o["race_events"][i] == 0:  # the reference is deterministic on this cloud -> exact
                 assert np.array_equal(npy(ra[i]), npy(a[i])) and np.array_equal(npy(rd[i]), npy(d[i]))
                 checked += 1
-        # statistical agreement on every cloud, racy or not: mean sqrt(dist) within 2 % and the
-        # reference's own invariant dist == |x1 - x2[asg]|^2 holds for both
+        # coarse sanity bound on every cloud, racy or not (the sharp statement is the envelope test below): mean
+        # sqrt(dist) within 2 %
         ours, theirs = npy(d).astype(np.float64), npy(rd).astype(np.float64)
         assert abs(np.sqrt(ours).mean() - np.sqrt(theirs).mean()) <= 0.02 * np.sqrt(theirs).mean()
     assert checked >= 12
+
+
+def expected_cluster_size(b, sm_count):
+    """pick_cluster (csrc/pcl_emd.cu): the largest power of two <= 16 with b * cs <= SM count."""
+    cs = 16
+    while cs > 1 and b * cs > sm_count:
+        cs >>= 1
+    return cs
+
+
+@pytest.mark.parametrize("b", [4, 16, 32, 40, 80])
+@pytest.mark.parametrize("regime", ["independent", "noisy"])
+def test_emd_bit_exact_at_every_cluster_size_on_the_bench_workload(b, regime):
+    """The launch bench.py times is B=32, N=2048 -> clusters of 4 CTAs; the dealing of the bidders to the CTAs of a
+    cluster depends on the cluster size, so every size (16, 8, 4, 2, 1) is checked against the oracle at N=2048 on
+    the bench's own clouds (bench.py make_pool: synth.table_clouds(32, 2048, seed=1000*rank+s, regime))."""
+    import ctypes
+    sm = ctypes.c_int(0)
+    pcl._lib.lib().pcl_device_info(ctypes.byref(sm), None, None, None)
+    for seed in ((0, 1, 2, 3) if b == 32 else (0,)):       # B=32: all four base batches of the bench pool
+        x1, t = synth.table_clouds(b, 2048, seed=seed, regime=regime)
+        x2 = t[:, :, :3].contiguous()
+        o = oracle.emd_forward(x1, x2, 0.005, 50, nthreads=16)
+        d, a, st = pcl.emd_forward_raw(x1.cuda(), x2.cuda(), 0.005, 50, want_stats=True)
+        st = npy(st)
+        assert (st[:, 3] == expected_cluster_size(b, sm.value)).all(), st[:, 3]
+        assert np.array_equal(npy(a), o["assignment"]) and np.array_equal(npy(d), o["dist"])
+        assert np.array_equal(st[:, 0], o["sum_unass"]) and np.array_equal(st[:, 1], o["iters_run"])
+
+
+def test_emd_deviation_lies_inside_the_reference_nondeterminism_envelope(ref_ext):
+    """The reference's GetMax lets the LAST writer inside a +-1e-6 window win (emd_cuda.cu:181-194): which bidder that is
+    depends on the thread order.  Every cloud without such an event must equal the unmodified reference bit for bit; for
+    the others our fixed rule (largest bidder index) must land inside the spread the reference itself shows when only
+    the ORDER of the predictions changes (same point sets, so the same problem; the rows are permuted back)."""
+    if ref_ext is None:
+        pytest.skip("oracle/_ref/emd.so not built (needs /root/reference at build time)")
+    b, n = 32, 2048
+    x1, t = synth.table_clouds(b, n, seed=0, regime="independent")   # pool[0] of bench.py
+    x2 = t[:, :, :3].contiguous()
+    o = oracle.emd_forward(x1, x2, 0.005, 50, nthreads=16)
+    d, a, _ = pcl.emd_forward_raw(x1.cuda(), x2.cuda(), 0.005, 50)
+    ours = np.sqrt(npy(d).astype(np.float64)).mean(1)                # per-cloud mean sqrt(dist)
+    g = torch.Generator().manual_seed(5)
+    runs = []
+    for r in range(8):
+        perm = torch.arange(n) if r < 3 else torch.randperm(n, generator=g)   # 3 plain repeats + 5 re-orderings
+        rd, ra = ref_emd_forward(ref_ext, x1[:, perm], x2, 0.005, 50)
+        inv = torch.empty_like(perm); inv[perm] = torch.arange(n)
+        rd, ra = npy(rd)[:, inv.numpy()], npy(ra)[:, inv.numpy()]
+        if r < 3:
+            for i in range(b):
+                if o["race_events"][i] == 0:
+                    assert np.array_equal(ra[i], npy(a[i])) and np.array_equal(rd[i], npy(d[i]))
+        runs.append(np.sqrt(rd.astype(np.float64)).mean(1))
+    runs = np.stack(runs)                                            # (8, B)
+    spread = runs.max(0) - runs.min(0)
+    dev = np.abs(ours - runs.mean(0))
+    racy = o["race_events"] > 0
+    print(f"race-free clouds: {int((~racy).sum())}/{b}; racy clouds: max deviation of ours from the reference mean "
+          f"{dev[racy].max() if racy.any() else 0:.3e}, reference spread min/median/max "
+          f"{np.min(spread[racy]) if racy.any() else 0:.3e}/{np.median(spread[racy]) if racy.any() else 0:.3e}/"
+          f"{np.max(spread[racy]) if racy.any() else 0:.3e}")
+    # a ninth draw from the reference's own distribution lies outside the range of eight with probability 2/9 per cloud, so
+    # the per-cloud bound is 3 ranges around the reference mean; the batch value (what the trainer sees) gets 2 ranges
+    assert (dev <= 3.0 * spread + 1e-9).all(), (dev, spread)
+    batch = runs.mean(1)
+    assert abs(ours.mean() - batch.mean()) <= 2.0 * (batch.max() - batch.min()) + 1e-9
 
 
 def test_emd_backward_matches_reference_and_oracle(ref_ext):

@@ -21,11 +21,17 @@ def _t(a):
     return torch.from_numpy(np.asarray(a))
 
 
+def reference_structure(eps, its, num_classes=None):
+    """The reference's own op-by-op loss structure (oracle/loss_oracle.py, utils.py:253-309) on top of the CUDA emdModule."""
+    mod = pcl.emdModule()
+    return loss_oracle.EarthMoverDistance(eps, its, num_classes, emd_fn=lambda a, b, e, i: mod(a, b, e, i))
+
+
 @pytest.mark.parametrize("fused", [True, False])
 @pytest.mark.parametrize("tag,C", [("ae", None), ("seg", 5)])
 def test_earth_mover_distance_matches_reference_python_golden(golden, tag, C, fused):
     pred = _t(golden[f"{tag}_pred"]).cuda().requires_grad_()
-    fn = pcl.EarthMoverDistance(eps=0.005, its=50, num_classes=C, fused=fused)
+    fn = pcl.EarthMoverDistance(eps=0.005, its=50, num_classes=C) if fused else reference_structure(0.005, 50, C)
     logged = {}
     fn.log = lambda k, v: logged.__setitem__(k, float(v.detach()))     # train.py:161
     loss = fn(pred, _t(golden[f"{tag}_target"]).cuda())
@@ -46,7 +52,8 @@ def test_fused_and_reference_structure_agree_at_full_size(C):
     out = []
     for fused in (True, False):
         p = pred.cuda().requires_grad_()
-        loss = pcl.EarthMoverDistance(0.005, 50, num_classes=C, fused=fused)(p, target.cuda())
+        fn = pcl.EarthMoverDistance(0.005, 50, num_classes=C) if fused else reference_structure(0.005, 50, C)
+        loss = fn(p, target.cuda())
         loss.backward()
         out.append((float(loss), npy(p.grad)))
     assert out[0][0] == pytest.approx(out[1][0], rel=REL)
@@ -113,7 +120,7 @@ def test_sqrt_at_zero_distance_behaves_like_the_reference():
     _, target = synth.autoencoder_batch(1, 1024, seed=3)
     for fused in (True, False):
         p = target.clone().cuda().requires_grad_()
-        loss = pcl.EarthMoverDistance(0.005, 50, fused=fused)(p, target.cuda())
+        loss = (pcl.EarthMoverDistance(0.005, 50) if fused else reference_structure(0.005, 50))(p, target.cuda())
         loss.backward()
         assert float(loss) == pytest.approx(0.0, abs=1e-6)
         assert not torch.isfinite(p.grad[:, :, :3]).all()
