@@ -123,42 +123,45 @@ def test_emd_bit_exact_at_every_cluster_size_on_the_bench_workload(b, regime):
 
 def test_emd_deviation_lies_inside_the_reference_nondeterminism_envelope(ref_ext):
     """The reference's GetMax lets the LAST writer inside a +-1e-6 window win (emd_cuda.cu:181-194): which bidder that is
-    depends on the thread order.  Every cloud without such an event must equal the unmodified reference bit for bit; for
-    the others our fixed rule (largest bidder index) must land inside the spread the reference itself shows when only
-    the ORDER of the predictions changes (same point sets, so the same problem; the rows are permuted back)."""
+    depends on the thread schedule, so the unmodified reference is not reproducible -- on the bench's early-training batch
+    every cloud has 8-37 such events and four IDENTICAL launches differ by up to 2 % in a cloud's mean sqrt(dist)
+    (measured: tools/envelope_probe.py).  Every cloud without an event must equal the reference bit for bit; on the others
+    our fixed rule (largest bidder index) must be one more draw from the reference's own distribution: per cloud and for
+    the batch value the trainer sees, our result lies within 5 sigma of the reference's runs (4 repeats + 8 re-orderings
+    of the predictions -- the same point sets, rows permuted back), sigma floored by the pooled per-cloud value."""
     if ref_ext is None:
         pytest.skip("oracle/_ref/emd.so not built (needs /root/reference at build time)")
     b, n = 32, 2048
-    x1, t = synth.table_clouds(b, n, seed=0, regime="independent")   # pool[0] of bench.py
-    x2 = t[:, :, :3].contiguous()
-    o = oracle.emd_forward(x1, x2, 0.005, 50, nthreads=16)
-    d, a, _ = pcl.emd_forward_raw(x1.cuda(), x2.cuda(), 0.005, 50)
-    ours = np.sqrt(npy(d).astype(np.float64)).mean(1)                # per-cloud mean sqrt(dist)
-    g = torch.Generator().manual_seed(5)
-    runs = []
-    for r in range(8):
-        perm = torch.arange(n) if r < 3 else torch.randperm(n, generator=g)   # 3 plain repeats + 5 re-orderings
-        rd, ra = ref_emd_forward(ref_ext, x1[:, perm], x2, 0.005, 50)
-        inv = torch.empty_like(perm); inv[perm] = torch.arange(n)
-        rd, ra = npy(rd)[:, inv.numpy()], npy(ra)[:, inv.numpy()]
-        if r < 3:
-            for i in range(b):
-                if o["race_events"][i] == 0:
+    for regime in ("independent", "noisy"):                              # pool[0] and pool[1] of bench.py
+        x1, t = synth.table_clouds(b, n, seed=0, regime=regime)
+        x2 = t[:, :, :3].contiguous()
+        o = oracle.emd_forward(x1, x2, 0.005, 50, nthreads=16)
+        d, a, _ = pcl.emd_forward_raw(x1.cuda(), x2.cuda(), 0.005, 50)
+        ours = np.sqrt(npy(d).astype(np.float64)).mean(1)                # per-cloud mean sqrt(dist)
+        racy = o["race_events"] > 0
+        g = torch.Generator().manual_seed(5)
+        runs = []
+        for r in range(12):
+            perm = torch.arange(n) if r < 4 else torch.randperm(n, generator=g)
+            rd, ra = ref_emd_forward(ref_ext, x1[:, perm], x2, 0.005, 50)
+            inv = torch.empty_like(perm)
+            inv[perm] = torch.arange(n)
+            rd, ra = npy(rd)[:, inv.numpy()], npy(ra)[:, inv.numpy()]
+            if r < 4:
+                for i in np.nonzero(~racy)[0]:                           # deterministic clouds: exact
                     assert np.array_equal(ra[i], npy(a[i])) and np.array_equal(rd[i], npy(d[i]))
-        runs.append(np.sqrt(rd.astype(np.float64)).mean(1))
-    runs = np.stack(runs)                                            # (8, B)
-    spread = runs.max(0) - runs.min(0)
-    dev = np.abs(ours - runs.mean(0))
-    racy = o["race_events"] > 0
-    print(f"race-free clouds: {int((~racy).sum())}/{b}; racy clouds: max deviation of ours from the reference mean "
-          f"{dev[racy].max() if racy.any() else 0:.3e}, reference spread min/median/max "
-          f"{np.min(spread[racy]) if racy.any() else 0:.3e}/{np.median(spread[racy]) if racy.any() else 0:.3e}/"
-          f"{np.max(spread[racy]) if racy.any() else 0:.3e}")
-    # a ninth draw from the reference's own distribution lies outside the range of eight with probability 2/9 per cloud, so
-    # the per-cloud bound is 3 ranges around the reference mean; the batch value (what the trainer sees) gets 2 ranges
-    assert (dev <= 3.0 * spread + 1e-9).all(), (dev, spread)
-    batch = runs.mean(1)
-    assert abs(ours.mean() - batch.mean()) <= 2.0 * (batch.max() - batch.min()) + 1e-9
+            runs.append(np.sqrt(rd.astype(np.float64)).mean(1))
+        runs = np.stack(runs)                                            # (12, B)
+        sigma = runs.std(0, ddof=1)
+        pooled = float(np.sqrt((sigma[racy] ** 2).mean())) if racy.any() else 0.0
+        dev = np.abs(ours - runs.mean(0))
+        print(f"[{regime}] race-free clouds {int((~racy).sum())}/{b} (bit-exact vs the reference); racy clouds: reference sigma "
+              f"pooled {pooled:.2e} (max {sigma.max():.2e}, identical-launch spread max {(runs[:4].max(0) - runs[:4].min(0)).max():.2e}), "
+              f"ours - reference mean: max {dev.max():.2e} = {np.max(dev / np.maximum(np.maximum(sigma, pooled), 1e-12)):.2f} sigma")
+        assert (dev[~racy] <= 1e-12).all()
+        assert (dev <= 5.0 * np.maximum(sigma, pooled) + 1e-12).all(), (dev, sigma, pooled)
+        batch = runs.mean(1)                                             # the loss value of the batch, per reference run
+        assert abs(ours.mean() - batch.mean()) <= 5.0 * batch.std(ddof=1) + 1e-12
 
 
 def test_emd_backward_matches_reference_and_oracle(ref_ext):

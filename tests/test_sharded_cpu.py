@@ -16,7 +16,8 @@ sys.path.insert(0, ROOT)
 
 import oracle  # noqa: E402
 from pointcloud_b200 import synth  # noqa: E402
-from pointcloud_b200.losses import ChamferDistance, EarthMoverDistance  # noqa: E402
+from pointcloud_b200.losses import (ChamferDistance, EarthMoverDistance, FilterClasses, FilteringChamferDistance,  # noqa: E402
+                                    SegmentingChamferDistance)
 from pointcloud_b200.sharded import ShardedLoss, shard_bounds  # noqa: E402
 
 
@@ -55,6 +56,20 @@ class CpuChamfer(ChamferDistance):
     def __call__(self, pred, target):
         from oracle import loss_oracle
         return loss_oracle.chamfer_distance(pred, target)[0]
+
+
+class CpuFilteringChamfer(FilteringChamferDistance):
+    """Product filter + pad logic (torch path on a CPU tensor), Chamfer arithmetic from the CPU oracle."""
+
+    def __call__(self, pred, target):
+        from oracle import loss_oracle
+        tgt, num = self._filter_pad(target, torch.float32)
+        return loss_oracle.chamfer_distance(pred.to(torch.float32), tgt, y_lengths=num)[0]
+
+
+class CpuSegmentingChamfer(SegmentingChamferDistance):
+    def __init__(self, class_labels):
+        self.classs_losses = {c: CpuFilteringChamfer(FilterClasses([l], label_dim=3)) for c, l in class_labels.items()}
 
 
 def _data(kind):
