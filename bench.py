@@ -3,13 +3,16 @@
 
 One "step" = one pass of the loss hot path over one batch of B=32 synthetic Table-shaped cloud pairs
 (N=M=2048): Chamfer fwd + bwd and auction EMD (eps=0.005, 50 iterations, cfg.py:36-37) fwd + bwd with the
-reference's sqrt-mean reduction (utils.py:304, weights == 1).  Weak scaling: every rank owns B=32 clouds.
+reference's sqrt-mean reduction (utils.py:304, weights == 1), through pointcloud_b200.ShardedChamferEmdStep: one C-ABI
+call (three kernels) per rank and, at N > 1, the one all-reduce of the batch sums INSIDE the timed region.
 
-  value : whole-job clouds/s with inputs resident in HBM, timed with CUDA events, max over ranks
+  value : whole-job clouds/s, WEAK scaling (32 clouds per rank), inputs resident in HBM, CUDA events, max over ranks
+  strong_scaling : the same step with B=32 GLOBAL (32/N clouds per rank)
   e2e   : the same metric through the C-ABI host-buffer entry point (pcl_chamfer_emd_step_host): pinned HOST inputs
           copied in, loss scalars copied back and the stream synchronised inside the timed region, every step
-          (e2e.python_api: the same through the Python loss classes)
-  roofline / cpu_baseline / reference_gpu : see DESIGN.md "Measurement"
+          (e2e.python_api: the same through the Python loss functions; sharded_api: the loss CLASSES through ShardedLoss)
+  parity_checked : the timed step's outputs against the CPU oracle (outside the timed regions)
+  roofline / roofline_bwd / cpu_baseline / reference_gpu : see DESIGN.md "Measurement"
 
 `--impl reference` times the reference's CPU path (the oracle port: the reference EMD has no CPU
 implementation and pytorch3d is absent) on the host cores, on a bounded sample of the same workload.
@@ -35,6 +38,7 @@ WORKLOAD = ("config2: Chamfer+EMD fwd+bwd, B=32 per GPU, N=M=2048, Table-shaped 
 FLOP_PER_EMD_EVAL = 11   # 8 (distance) + sqrt + 2 adds
 FLOP_PER_CHAMFER_EVAL = 8
 NCU_AUCTION_DRAM_BYTES = 1670656  # ncu --set full, one launch (profiles/r1_s2_emd_auction_full.txt)
+KERNELS_PER_STEP = 3  # emd_auction_kernel (fused epilogue) | chamfer_nn3_kernel, chamfer_bwd_kernel (side stream); + 4 small memsets
 
 
 def peaks():
@@ -118,53 +122,42 @@ def make_pool(torch, synth, device, rank, n_sets):
     return pool
 
 
-class DeviceStep:
-    """The hot path through the C ABI with preallocated outputs (no Python allocation in the timed region)."""
-    # fill2, chamfer_nn3, chamfer_finish, chamfer_bwd (side stream) | emd_auction, wreduce_stage1, wreduce_stage2, emd_weighted_bwd, emd_mean
-    KERNELS_PER_STEP = 9
+class DeviceKernels:
+    """The separate C-ABI entry points with preallocated outputs, for the per-phase breakdown and the kernel rooflines."""
 
-    def __init__(self, torch, _lib, device):
-        self.torch, self.lib, self.L = torch, _lib, _lib.lib()
-        b, n = B_PER_GPU, NPTS
+    def __init__(self, torch, _lib, device, b=B_PER_GPU, n=NPTS):
+        self.torch, self.lib, self.L, self.b, self.n = torch, _lib, _lib.lib(), b, n
         f32, i32 = torch.float32, torch.int32
         e = lambda *s, dt=f32: torch.empty(*s, device=device, dtype=dt)
         self.dist_x, self.dist_y, self.idx_x, self.idx_y = e(b, n), e(b, n), e(b, n, dt=i32), e(b, n, dt=i32)
-        self.loss_xy, self.ones = e(2), torch.ones(2, device=device)
+        self.loss_xy, self.ones = e(4), torch.ones(2, device=device)
         self.gx, self.gy = e(b, n, 3), e(b, n, 3)
         self.dist, self.asg, self.stats = e(b, n), e(b, n, dt=i32), e(b, 8, dt=i32)
-        self.sums, self.gemd = e(2), e(b, n, 3)
+        self.sums, self.gemd, self.graddist = e(4), e(b, n, 3), torch.full((b, n), 1.0 / (b * n), device=device)
         self.cws = self.L.pcl_chamfer_workspace_bytes(b, n, n); self.cw = torch.empty(self.cws, device=device, dtype=torch.uint8)
         self.ews = self.L.pcl_emd_workspace_bytes(b, n); self.ew = torch.empty(self.ews, device=device, dtype=torch.uint8)
-        self.sws = self.L.pcl_chamfer_emd_step_scratch_bytes(b, n); self.sw = torch.empty(self.sws, device=device, dtype=torch.uint8)
-        self.losses = e(4)
 
-    def chamfer(self, p, t, st):
-        L, A, b, n = self.L, self.lib.pts_args, B_PER_GPU, NPTS
-        rc = L.pcl_chamfer_fwd(*A(p), None, *A(t), None, b, n, n, 3, 0, self.dist_x.data_ptr(), self.idx_x.data_ptr(),
-                               self.dist_y.data_ptr(), self.idx_y.data_ptr(), self.loss_xy.data_ptr(), self.cw.data_ptr(), self.cws, st)
-        rc |= L.pcl_chamfer_bwd(*A(p), None, *A(t), None, b, n, n, 3, self.idx_x.data_ptr(), self.idx_y.data_ptr(),
-                                self.ones.data_ptr(), self.gx.data_ptr(), self.gy.data_ptr(), st)
-        return rc
+    def chamfer_fwd(self, p, t, st):
+        A, b, n = self.lib.pts_args, self.b, self.n
+        return self.L.pcl_chamfer_fwd(*A(p), None, *A(t), None, b, n, n, 3, 0, self.dist_x.data_ptr(), self.idx_x.data_ptr(),
+                                      self.dist_y.data_ptr(), self.idx_y.data_ptr(), self.loss_xy.data_ptr(), self.cw.data_ptr(), self.cws, st)
 
-    def emd_fwd(self, p, t, st):
-        A, b, n = self.lib.pts_args, B_PER_GPU, NPTS
-        return self.L.pcl_emd_fwd(*A(p), *A(t), b, n, EPS, ITERS, self.dist.data_ptr(), self.asg.data_ptr(),
-                                  self.stats.data_ptr(), self.ew.data_ptr(), self.ews, st)
+    def chamfer_bwd(self, p, t, st):
+        A, b, n = self.lib.pts_args, self.b, self.n
+        return self.L.pcl_chamfer_bwd(*A(p), None, *A(t), None, b, n, n, 3, self.idx_x.data_ptr(), self.idx_y.data_ptr(),
+                                      self.ones.data_ptr(), self.gx.data_ptr(), self.gy.data_ptr(), st)
 
-    def emd_rest(self, p, t, st):
-        L, A, b, n = self.L, self.lib.pts_args, B_PER_GPU, NPTS
-        rc = L.pcl_emd_weighted_reduce(self.dist.data_ptr(), None, None, b, n, 0, self.sums.data_ptr(), self.ew.data_ptr(), self.ews, st)
-        rc |= L.pcl_emd_weighted_bwd(*A(p), *A(t), b, n, self.asg.data_ptr(), self.dist.data_ptr(), None, None, 0,
-                                     self.sums.data_ptr(), self.ones.data_ptr(), self.gemd.data_ptr(), st)
-        return rc
+    def emd_fused(self, p, t, st, stats=True):
+        """auction + CalcDist + sqrt-mean + gradient of the mean: the whole EMD side of the step, one kernel"""
+        A, b, n = self.lib.pts_args, self.b, self.n
+        return self.L.pcl_emd_fwd_fused(*A(p), *A(t), b, n, EPS, ITERS, self.dist.data_ptr(), self.asg.data_ptr(),
+                                        self.stats.data_ptr() if stats else None, 1.0 / (b * n), self.gemd.data_ptr(), self.sums.data_ptr(),
+                                        self.ew.data_ptr(), self.ews, st)
 
-    def __call__(self, p, t, st):
-        """The whole step in ONE C-ABI call (pcl_chamfer_emd_step): Chamfer on the library's side stream next to the auction."""
-        A = self.lib.pts_args
-        rc = self.L.pcl_chamfer_emd_step(*A(p), *A(t), B_PER_GPU, NPTS, EPS, ITERS, 0, self.losses.data_ptr(), self.gx.data_ptr(),
-                                         self.gemd.data_ptr(), self.sw.data_ptr(), self.sws, st)
-        if rc:
-            raise RuntimeError(self.L.pcl_last_error().decode())
+    def emd_bwd(self, p, t, st):
+        """the module-level backward (emdFunction.backward): gather/scatter kernel alone"""
+        A, b, n = self.lib.pts_args, self.b, self.n
+        return self.L.pcl_emd_bwd(*A(p), *A(t), b, n, self.asg.data_ptr(), self.graddist.data_ptr(), self.gemd.data_ptr(), st)
 
 
 # ------------------------------------------------------------------------------------------------ CPU baseline
@@ -224,6 +217,74 @@ def run_reference(args):
     print(json.dumps(line))
 
 
+# ------------------------------------------------------------------------------------------------ parity / reference
+def parity_check(torch, np, pcl, pool, device):
+    """Outside every timed region: the composite step of the first early-training and the first late-training batch of the
+    pool against the CPU oracle (bit-exact assignment and distances, loss scalars and gradients within 1e-5 relative)."""
+    import oracle
+    step = pcl.ShardedChamferEmdStep(B_PER_GPU, NPTS, device, EPS, ITERS, process_group=None)
+    step.world = 1
+    kern_dist = torch.empty(B_PER_GPU, NPTS, device=device)
+    out = {}
+    for p, t, regime in pool[:2]:
+        step.step(p, t)
+        torch.cuda.synchronize()
+        got = step.out.cpu().double().numpy()
+        x1, x2 = p.cpu(), t.cpu()
+        o = oracle.emd_forward(x1, x2, EPS, ITERS, nthreads=os.cpu_count() or 1)
+        d, a, _ = pcl.emd_forward_raw(p, t, EPS, ITERS)
+        exact = bool(np.array_equal(a.cpu().numpy(), o["assignment"]) and np.array_equal(d.cpu().numpy(), o["dist"]))
+        sq = np.sqrt(o["dist"].astype(np.float64))
+        emd_ok = abs(got[6] - sq.mean()) <= 1e-5 * sq.mean() and abs(got[4] - sq.sum()) <= 1e-5 * sq.sum() and got[5] == B_PER_GPU * NPTS
+        gd = ((1.0 / o["dist"].size) / (2.0 * np.sqrt(o["dist"]))).astype(np.float32)
+        g1, _ = oracle.emd_backward(x1, x2, o["assignment"], gd)
+        ge = step.grad_emd.cpu().numpy()
+        grad_emd_ok = bool(np.allclose(ge, g1, rtol=1e-5, atol=1e-12))
+        c = oracle.chamfer_forward(x1, x2, nthreads=os.cpu_count() or 1)
+        ch_ok = abs(got[0] + got[1] - float(c["loss"])) <= 1e-5 * float(c["loss"])
+        gx, _ = oracle.chamfer_backward(x1, x2, c["idx_x"], c["idx_y"], 1.0)
+        gc = step.grad_chamfer.cpu().numpy()
+        grad_ch_ok = bool(np.allclose(gc, gx, rtol=1e-5, atol=1e-6 * float(np.abs(gx).max())))
+        out[regime] = {"emd_assignment_and_dist_bit_exact": exact, "emd_loss": bool(emd_ok), "emd_grad": grad_emd_ok,
+                       "chamfer_loss": bool(ch_ok), "chamfer_grad": grad_ch_ok, "race_free_clouds": int((o["race_events"] == 0).sum())}
+    ok = all(v for r in out.values() for k, v in r.items() if k != "race_free_clouds")
+    return ok, out
+
+
+def reference_gpu_step(torch, pool, ev, emd_ms_ours):
+    """The UNMODIFIED reference CUDA extension (oracle/_ref/emd.so) driven exactly like the reference's emd_module.py drives it --
+    emdFunction.forward (12 zero-filled scratch tensors + emd.forward, emd_module.py:33-61), `dists.sqrt().mean()` (utils.py:304
+    with weights == 1) and its backward through emdFunction.backward (2 more zero fills + emd.backward, :63-72) -- on the same
+    B200, over the same pool, both regimes, >= 20 steps each.  Context for the speed-up, outside our timed regions."""
+    from oracle import build_ref
+    ref = build_ref.load_ref()
+    if ref is None:
+        return {"unavailable": "oracle/_ref/emd.so was not built (needs /root/reference at build time)"}
+    sys.path.insert(0, os.path.join(ROOT, "tests"))
+    from helpers import RefEmdFunction
+    out = {"what": "unmodified reference emd extension (oracle/_ref/emd.so) under a restatement of emdFunction (tests/helpers.py): forward "
+                   "(12 torch.zeros + 351 launches) + dists.sqrt().mean() + backward, same B200, same pool"}
+    for regime in ("independent", "noisy"):
+        sets = [(p, t) for p, t, r in pool if r == regime][:24]
+        ts = []
+        for i, (p, t) in enumerate(sets):
+            x = p.detach().clone().requires_grad_()
+            a, b_ = ev(), ev()
+            a.record()
+            dist, _ = RefEmdFunction.apply(ref, x, t, EPS, ITERS)
+            dist.sqrt().mean().backward()
+            b_.record()
+            torch.cuda.synchronize()
+            if i >= 4:
+                ts.append(a.elapsed_time(b_))
+        out[f"emd_step_ms_{regime}"] = statistics.mean(ts)
+        out[f"steps_{regime}"] = len(ts)
+    out["emd_step_ms"] = 0.5 * (out["emd_step_ms_independent"] + out["emd_step_ms_noisy"])
+    out["ours_emd_step_ms"] = emd_ms_ours
+    out["emd_step_speedup"] = out["emd_step_ms"] / emd_ms_ours
+    return out
+
+
 # ------------------------------------------------------------------------------------------------ main arm
 def main():
     ap = argparse.ArgumentParser()
@@ -232,7 +293,7 @@ def main():
     ap.add_argument("--warmup", type=int, default=5)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
-    ap.add_argument("--profile", action="store_true", help="value leg + breakdown only (short command for ncu)")
+    ap.add_argument("--profile", action="store_true", help="value leg only (short command for ncu)")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3)
     if args.impl == "reference":
@@ -279,66 +340,125 @@ def main():
             return float(t.item())
         return x
 
+    def timed(fn, k, w):
+        """w untimed + k timed calls of fn(i), barrier + synchronise on both sides, CUDA events, max over ranks -> total ms"""
+        for i in range(w):
+            fn(i)
+        barrier()
+        e0, e1 = ev(), ev()
+        e0.record()
+        for i in range(k):
+            fn(w + i)
+        e1.record()
+        barrier()
+        return max_over_ranks(e0.elapsed_time(e1))
+
     K, W = args.steps, args.warmup
     sampler = ClockSampler(local)
     sampler.start()  # started early: nvidia-smi needs a few hundred ms before its first sample
     n_sets = 96  # 96 * 1.57 MB of inputs = 151 MB > 126 MB L2: every step reads inputs that are not L2-resident
     pool = make_pool(torch, synth, device, rank, n_sets)
-    step = DeviceStep(torch, _lib, device)
     st = torch.cuda.current_stream().cuda_stream
     ev = lambda: torch.cuda.Event(enable_timing=True)
 
-    # ---- value: device-resident inputs, whole step, CUDA events on the launching stream ---------------
-    for i in range(W):
-        step(*pool[i % n_sets][:2], st)
-    barrier()
+    # ---- value (weak scaling, 32 clouds per GPU): the sharded config-2 step of the product package.  Per step and rank: ONE C-ABI
+    #      call (three kernels: auction with fused epilogue | Chamfer forward, Chamfer backward on the side stream) + at N > 1 ONE
+    #      NCCL all-reduce of the four batch sums, INSIDE the timed region --------------------------------------------------------
+    step = pcl.ShardedChamferEmdStep(B_PER_GPU, NPTS, device, EPS, ITERS)
     t_wall0 = time.time()
-    e0, e1 = ev(), ev()
-    e0.record()
-    for i in range(K):
-        step(*pool[(W + i) % n_sets][:2], st)
-    e1.record()
-    barrier()
+    ms_total = timed(lambda i: step.step(*pool[i % n_sets][:2]), K, W)
     t_wall1 = time.time()
-    ms_total = max_over_ranks(e0.elapsed_time(e1))
     clocks = sampler.stop(t_wall0, t_wall1)
     ms_per_step = ms_total / K
     value = world * B_PER_GPU * K / (ms_total * 1e-3)
+    if args.profile:
+        if rank == 0:
+            print(json.dumps({"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": K, "ms_per_step": ms_per_step, "profile_only": True}))
+        if world > 1:
+            dist.destroy_process_group()
+        return
 
-    # ---- per-kernel breakdown on rank 0's stream (explains `value`; same inputs, the phases run one after the other
-    #      here, whereas the timed step above overlaps Chamfer with the auction) ----
-    phases = {"chamfer_fwd_bwd": [], "emd_fwd": [], "emd_reduce_bwd": []}
+    # the collective alone, and the sharded step against one GPU on the gathered batch (outside the timed regions)
+    coll_ms, sharded_equals_single = None, None
+    if world > 1:
+        tiny = torch.zeros(4, device=device)
+        coll_ms = timed(lambda i: dist.all_reduce(tiny), 200, 20) / 200
+        p, t, _ = pool[0]
+        step.step(p, t)
+        got = step.losses()
+        gp = [torch.empty_like(p) for _ in range(world)]
+        gt = [torch.empty_like(t) for _ in range(world)]
+        dist.all_gather(gp, p.contiguous()); dist.all_gather(gt, t.contiguous())
+        if rank == 0:
+            single = pcl.ShardedChamferEmdStep(world * B_PER_GPU, NPTS, device, EPS, ITERS)
+            single.world = 1
+            single.step(torch.cat(gp), torch.cat(gt))
+            want = single.losses()
+            sharded_equals_single = {k: abs(got[k] - want[k]) <= 1e-5 * abs(want[k]) for k in want}
+            lo = rank * B_PER_GPU
+            sharded_equals_single["grad_emd"] = bool(torch.allclose(step.grad_emd, single.grad_emd[lo:lo + B_PER_GPU] * world, rtol=1e-5, atol=1e-12))
+            sharded_equals_single["grad_chamfer"] = bool(torch.allclose(step.grad_chamfer, single.grad_chamfer[lo:lo + B_PER_GPU] * world, rtol=1e-5, atol=1e-9))
+            assert all(sharded_equals_single.values()), sharded_equals_single
+            del single
+        barrier()
+
+    # ---- strong scaling (BASELINE.json: "(B=32,N=2048) at 1/2/4/8 B200" read as B=32 GLOBAL): 32 / N clouds per rank ------------
+    strong = None
+    if B_PER_GPU % world == 0:
+        bl = B_PER_GPU // world
+        sstep = pcl.ShardedChamferEmdStep(bl, NPTS, device, EPS, ITERS)
+        lo = rank * bl
+        if world == 1:
+            spool = [(p, t) for p, t, _ in pool]
+        else:  # every rank holds its slice of the SAME global batches: rank 0's pool
+            spool = []
+            for p, t, _ in pool[:32]:
+                pp, tt = p.clone(), t.clone()
+                dist.broadcast(pp, 0); dist.broadcast(tt, 0)
+                spool.append((pp[lo:lo + bl].contiguous(), tt[lo:lo + bl].contiguous()))
+        Ks = min(K, 200)
+        s_ms = timed(lambda i: sstep.step(*spool[i % len(spool)]), Ks, W)
+        strong = {"global_batch": B_PER_GPU, "clouds_per_gpu": bl, "steps": Ks, "ms_per_step": s_ms / Ks, "value": B_PER_GPU * Ks / (s_ms * 1e-3),
+                  "unit": UNIT, "scaling": "strong",
+                  "note": "same sharded step, B=32 split over the ranks; the auction takes B_r*cs SMs with cs <= 16 (cluster limit): "
+                          f"{bl} clouds per GPU use at most {min(148, bl * 16)} of 148 SMs"}
+        del sstep, spool
+
+    # ---- per-kernel breakdown on rank 0's stream (explains `value`; the phases run one after the other here, whereas the
+    #      timed step overlaps Chamfer with the auction) ----
+    kern = DeviceKernels(torch, _lib, device)
+    phases = {"chamfer_fwd": [], "chamfer_bwd": [], "emd_fused_fwd_bwd": [], "emd_bwd_kernel_alone": []}
     per_regime = {"independent": [], "noisy": []}
-    sum_u, executed, seq_ms = [], [], []
+    sum_u, executed = [], []
     for i in range(min(K, 32)):
         p, t, regime = pool[(W + i) % n_sets]
-        a, b_, c, d = ev(), ev(), ev(), ev()
-        a.record(); step.chamfer(p, t, st); b_.record(); step.emd_fwd(p, t, st); c.record(); step.emd_rest(p, t, st); d.record()
+        m = [ev() for _ in range(5)]
+        m[0].record(); rc = kern.chamfer_fwd(p, t, st); m[1].record(); rc |= kern.chamfer_bwd(p, t, st); m[2].record()
+        rc |= kern.emd_fused(p, t, st); m[3].record(); rc |= kern.emd_bwd(p, t, st); m[4].record()
         torch.cuda.synchronize()
-        per_regime_seq = a.elapsed_time(d)
-        phases["chamfer_fwd_bwd"].append(a.elapsed_time(b_)); phases["emd_fwd"].append(b_.elapsed_time(c)); phases["emd_reduce_bwd"].append(c.elapsed_time(d))
+        if rc:
+            raise RuntimeError(_lib.lib().pcl_last_error().decode())
+        for name, a, b_ in zip(phases, m[:-1], m[1:]):
+            phases[name].append(a.elapsed_time(b_))
         e_a, e_b = ev(), ev()
-        e_a.record(); step(p, t, st); e_b.record()
+        e_a.record(); step.step(p, t); e_b.record()
         torch.cuda.synchronize()
         per_regime[regime].append(e_a.elapsed_time(e_b))
-        seq_ms.append(per_regime_seq)
-        if step.chamfer(p, t, st) | step.emd_fwd(p, t, st) | step.emd_rest(p, t, st):
-            raise RuntimeError(_lib.lib().pcl_last_error().decode())
-        torch.cuda.synchronize()
-        sum_u.append(int(step.stats[:, 0].sum().item()))
-        executed.append(int(((step.stats[:, 4].long() & 0xffffffff) + (step.stats[:, 5].long() << 32)).sum().item()))
-    emd_ms = statistics.mean(phases["emd_fwd"])
-    evals = statistics.mean(sum_u) * NPTS  # pair evaluations one auction launch executes (sum_t U_t * N over the batch)
+        sum_u.append(int(kern.stats[:, 0].sum().item()))
+        executed.append(int(((kern.stats[:, 4].long() & 0xffffffff) + (kern.stats[:, 5].long() << 32)).sum().item()))
+    emd_ms = statistics.mean(phases["emd_fused_fwd_bwd"])
+    evals = statistics.mean(sum_u) * NPTS  # pair evaluations one auction launch stands for (sum_t U_t * N over the batch)
     sm_count = ctypes.c_int(0)
     _lib.lib().pcl_device_info(ctypes.byref(sm_count), None, None, None)
     pk = peaks()
     sm_max = pk.get("sm_max_mhz") or clocks.get("sm_max_mhz") or 1965.0
+    hbm_peak = pk.get("hbm_gbs") or 6532.0
     fp32_peak_tflops = sm_count.value * 128 * 2 * sm_max * 1e6 / 1e12
     achieved = FLOP_PER_EMD_EVAL * evals / (emd_ms * 1e-3) / 1e12
-    roofline = {"kernel": "emd_auction_kernel", "bound": "fp32-cuda-core", "achieved": achieved, "peak": fp32_peak_tflops,
-                "unit": "TFLOP/s", "frac": achieved / fp32_peak_tflops, "traffic": NCU_AUCTION_DRAM_BYTES,
-                "traffic_source": "dram__bytes_read.sum + dram__bytes_write.sum of one launch, profiles/r1_s2_emd_auction_full.txt "
-                                  "(algorithmic: 1.57 MB inputs + 0.52 MB outputs; the auction state never leaves shared memory)",
+    roofline = {"kernel": "emd_auction_kernel (with the fused CalcDist / sqrt-mean / gradient epilogue)", "bound": "fp32-cuda-core", "achieved": achieved,
+                "peak": fp32_peak_tflops, "unit": "TFLOP/s", "frac": achieved / fp32_peak_tflops, "traffic": NCU_AUCTION_DRAM_BYTES,
+                "traffic_source": "dram__bytes_read.sum + dram__bytes_write.sum of one launch, profiles/ (algorithmic: 1.57 MB inputs + 1.3 MB "
+                                  "outputs; the auction state never leaves shared memory)",
                 "peak_source": f"{sm_count.value} SMs x 128 lanes x 2 FLOP x {sm_max:.0f} MHz (MEASURED_PEAKS.json sm_max_mhz); "
                                "contraction depth 3 => CUDA-core bound, neither hbm nor tensor (SURVEY.md 8d)",
                 "algorithmic": f"{FLOP_PER_EMD_EVAL} FLOP x N x sum_t U_t = {FLOP_PER_EMD_EVAL * evals:.3e} FLOP per launch",
@@ -346,72 +466,73 @@ def main():
                 "executed_fraction": statistics.mean(executed) / evals,
                 "executed_note": "algorithmic = every (bidder, target) pair of the reference's Bid (N * sum_t U_t); the kernel proves "
                                  "whole 32-target tiles irrelevant with an exact bounding-box test and really evaluates only this fraction"}
-    # secondary roofline: the Chamfer forward kernel alone (FP32 CUDA-core bound as well).  `achieved` counts the ALGORITHMIC 8 FLOP
-    # per directed evaluation; the kernel executes 3 FFMA2-halves (6 FLOP) per evaluation in its approximate scan and
-    # the exact arithmetic only for the candidate chunks, so `executed_fma_lane_ops_frac` (3 FMA-pipe lane-ops per evaluation against
-    # the 128 lanes/clk/SM) is the pipe utilisation the scan itself accounts for; ncu: profiles/r1_s2_chamfer_nn3_full.txt
-    tch = []
-    for i in range(min(K, 32)):
-        p, t, _ = pool[(W + i) % n_sets]
-        a, b_ = ev(), ev()
-        a.record()
-        rc = step.L.pcl_chamfer_fwd(*_lib.pts_args(p), None, *_lib.pts_args(t), None, B_PER_GPU, NPTS, NPTS, 3, 0, step.dist_x.data_ptr(),
-                                    step.idx_x.data_ptr(), step.dist_y.data_ptr(), step.idx_y.data_ptr(), step.loss_xy.data_ptr(),
-                                    step.cw.data_ptr(), step.cws, st)
-        b_.record()
-        torch.cuda.synchronize()
-        assert rc == 0
-        tch.append(a.elapsed_time(b_))
     ch_evals = 2.0 * B_PER_GPU * NPTS * NPTS
-    ch_ms = statistics.mean(tch)
+    ch_ms = statistics.mean(phases["chamfer_fwd"])
     ch_achieved = FLOP_PER_CHAMFER_EVAL * ch_evals / (ch_ms * 1e-3) / 1e12
-    roofline_chamfer = {"kernel": "chamfer_nn3_kernel (+memset, finish)", "bound": "fp32-cuda-core", "achieved": ch_achieved, "peak": fp32_peak_tflops,
-                        "unit": "TFLOP/s", "frac": ch_achieved / fp32_peak_tflops, "traffic": None, "avg_launch_ms": ch_ms,
+    roofline_chamfer = {"kernel": "chamfer_nn3_kernel (one launch incl. the final reduction; + a 4-byte ticket memset)", "bound": "fp32-cuda-core",
+                        "achieved": ch_achieved, "peak": fp32_peak_tflops, "unit": "TFLOP/s", "frac": ch_achieved / fp32_peak_tflops, "traffic": None,
+                        "avg_launch_ms": ch_ms,
                         "algorithmic": f"{FLOP_PER_CHAMFER_EVAL} FLOP x 2*B*N*M directed evaluations = {FLOP_PER_CHAMFER_EVAL * ch_evals:.3e} FLOP per launch",
                         "executed_fma_lane_ops_frac": 3 * ch_evals / (ch_ms * 1e-3) / (fp32_peak_tflops * 1e12 / 2)}
+    # backward kernels: gather / scatter, bounded by the memory system (56 B per point and direction for Chamfer, 44 B per
+    # point for EMD).  The whole working set (3-7 MB) is L2-resident, so HBM never sees most of it: the fraction of the HBM copy peak is
+    # reported as asked, the limiter is L2 / atomic latency, not DRAM bandwidth (ncu lts counters in profiles/).
+    chb_ms, emb_ms = statistics.mean(phases["chamfer_bwd"]), statistics.mean(phases["emd_bwd_kernel_alone"])
+    chb_bytes, emb_bytes = 2.0 * B_PER_GPU * NPTS * 56, 1.0 * B_PER_GPU * NPTS * 44
+    roofline_bwd = {
+        "chamfer_bwd_kernel (+ 2 zero fills)": {"bound": "hbm", "achieved": chb_bytes / (chb_ms * 1e-3) / 1e9, "peak": hbm_peak, "unit": "GB/s",
+                                                "frac": chb_bytes / (chb_ms * 1e-3) / 1e9 / hbm_peak, "avg_launch_ms": chb_ms,
+                                                "algorithmic": f"2*B*N*56 B = {chb_bytes / 1e6:.2f} MB per launch", "traffic": None},
+        "emd_bwd_kernel": {"bound": "hbm", "achieved": emb_bytes / (emb_ms * 1e-3) / 1e9, "peak": hbm_peak, "unit": "GB/s",
+                           "frac": emb_bytes / (emb_ms * 1e-3) / 1e9 / hbm_peak, "avg_launch_ms": emb_ms,
+                           "algorithmic": f"B*N*44 B = {emb_bytes / 1e6:.2f} MB per launch", "traffic": None,
+                           "note": "module-level emdFunction.backward only; in the timed step the EMD gradient is written by the auction kernel's epilogue"},
+        "note": "both working sets are L2-resident (126 MB L2): latency / atomic bound, not DRAM bound"}
     breakdown = {k: statistics.mean(v) for k, v in phases.items()}
     breakdown["ms_per_step_independent"] = statistics.mean(per_regime["independent"]) if per_regime["independent"] else None
     breakdown["ms_per_step_noisy"] = statistics.mean(per_regime["noisy"]) if per_regime["noisy"] else None
-    breakdown["chamfer_directed_pair_evals_per_s"] = ch_evals / (breakdown["chamfer_fwd_bwd"] * 1e-3)
-    breakdown["ms_per_step_phases_run_sequentially"] = statistics.mean(seq_ms)
+    breakdown["chamfer_directed_pair_evals_per_s"] = ch_evals / (ch_ms * 1e-3)
+    breakdown["ms_per_step_phases_run_sequentially"] = breakdown["chamfer_fwd"] + breakdown["chamfer_bwd"] + breakdown["emd_fused_fwd_bwd"]
+    breakdown["collective_ms"] = coll_ms
 
     # ---- e2e: HOST buffers in, HOST results out, every step, through the C ABI (pcl_chamfer_emd_step_host) ------
-    # timed region per step: H2D of that step's pinned inputs, all 7 kernels, D2H of the three loss scalars, stream sync
+    # timed region per step: H2D of that step's pinned inputs, the three kernels, (N > 1: the all-reduce of the batch sums,) D2H of the
+    # loss vector, stream sync
     host = [(p.cpu().pin_memory(), t.cpu().pin_memory()) for p, t, _ in pool[:16]]
     L = _lib.lib()
     nbytes = L.pcl_loss_host_scratch_bytes(B_PER_GPU, NPTS)
     scratch = torch.empty(nbytes, dtype=torch.uint8, device=device)
-    loss_h = torch.zeros(4).pin_memory()
+    loss_h = torch.zeros(8).pin_memory()
+    red_d, red_h = torch.zeros(4, device=device), torch.zeros(4).pin_memory()
     cur_stream = torch.cuda.current_stream()
 
-    def host_step(ph, th):
+    def host_step(i):
+        ph, th = host[i % len(host)]
         rc = L.pcl_chamfer_emd_step_host(ph.data_ptr(), th.data_ptr(), B_PER_GPU, NPTS, EPS, ITERS, 0, loss_h.data_ptr(), None, None,
                                          scratch.data_ptr(), nbytes, st)
         if rc:
             raise RuntimeError(L.pcl_last_error().decode())
         cur_stream.synchronize()  # the caller reads loss_h now
-        return float(loss_h[0]) + float(loss_h[1]) + float(loss_h[2])
+        if world > 1:             # the sharded caller's collective on the four batch sums, result read back
+            red_d.copy_(loss_h[2:6], non_blocking=True)
+            dist.all_reduce(red_d)
+            red_h.copy_(red_d, non_blocking=True)
+            cur_stream.synchronize()
+            return float(red_h[2] / red_h[3])
+        return float(loss_h[0]) + float(loss_h[1]) + float(loss_h[6])
 
     Ke = max(8, min(K, 200))
-    for i in range(3):
-        host_step(*host[i % len(host)])
-    barrier()
-    e0, e1 = ev(), ev()
-    e0.record()
-    for i in range(Ke):
-        host_step(*host[i % len(host)])
-    e1.record()
-    barrier()
-    e2e_ms = max_over_ranks(e0.elapsed_time(e1))
+    e2e_ms = timed(host_step, Ke, 3)
     e2e = {"value": world * B_PER_GPU * Ke / (e2e_ms * 1e-3), "unit": UNIT, "h2d_bytes_per_step": 2 * B_PER_GPU * NPTS * 3 * 4,
-           "d2h_bytes_per_step": 12, "steps": Ke, "ms_per_step": e2e_ms / Ke,
-           "path": "C ABI pcl_chamfer_emd_step_host: pinned host inputs -> H2D -> Chamfer fwd+bwd, EMD fwd, sqrt-mean, EMD bwd -> D2H of the 3 loss "
-                   "scalars -> stream sync, every step (gradients stay on the device, as in training)"}
+           "d2h_bytes_per_step": 32, "steps": Ke, "ms_per_step": e2e_ms / Ke,
+           "path": "C ABI pcl_chamfer_emd_step_host: pinned host inputs -> H2D -> auction with fused epilogue | Chamfer fwd, Chamfer bwd -> D2H of the "
+                   "8-float loss vector -> stream sync, every step (gradients stay on the device, as in training)"}
 
     # ---- the same through the Python loss API (autograd Functions), for the torch user -----------------------------
     emd_mod = pcl.emdModule()
 
-    def api_step(ph, th):
+    def api_step(i):
+        ph, th = host[i % len(host)]
         p = ph.to(device, non_blocking=True).requires_grad_()
         t = th.to(device, non_blocking=True)
         closs, _ = pcl.chamfer_distance(p, t)
@@ -421,39 +542,38 @@ def main():
         return torch.stack([closs.detach(), eloss.detach()]).cpu()  # device -> host read of the step's result (synchronises)
 
     Kp = max(8, min(K, 40))
-    for i in range(3):
-        api_step(*host[i % len(host)])
-    barrier()
-    e0, e1 = ev(), ev()
-    e0.record()
-    for i in range(Kp):
-        api_step(*host[i % len(host)])
-    e1.record()
-    barrier()
-    api_ms = max_over_ranks(e0.elapsed_time(e1))
+    api_ms = timed(api_step, Kp, 3)
     e2e["python_api"] = {"value": world * B_PER_GPU * Kp / (api_ms * 1e-3), "ms_per_step": api_ms / Kp, "steps": Kp,
                          "path": "pointcloud_b200.chamfer_distance + emdModule + autograd, pinned host inputs, losses read back"}
 
-    # ---- the unmodified reference CUDA extension on the same GPU (EMD forward only; context, not the target) ----
-    reference_gpu = None
-    cb = None
+    # ---- the loss CLASSES train.py uses, through ShardedLoss, fwd + bwd, collectives inside the timed region (config 3 = Segmenter) ----
+    def class_leg(make_batch, loss_fn):
+        sh = pcl.ShardedLoss(loss_fn)
+        data = []
+        for s_ in range(2):
+            for regime in ("independent", "noisy"):
+                pr, tg = make_batch(B_PER_GPU, NPTS, seed=1000 * rank + s_, regime=regime)
+                data.append((pr.to(device), tg.to(device)))
+
+        def fn(i):
+            pr, tg = data[i % len(data)]
+            x = pr.detach().requires_grad_()
+            sh(x, tg).backward()
+        k = max(8, min(K, 40))
+        ms = timed(fn, k, 3)
+        return {"ms_per_step": ms / k, "value": world * B_PER_GPU * k / (ms * 1e-3), "unit": UNIT, "steps": k}
+    sharded_api = {
+        "autoencoder_loss (EarthMoverDistance, 1 all-reduce per call)": class_leg(synth.autoencoder_batch, pcl.EarthMoverDistance(EPS, ITERS)),
+        "segmenter_loss = config 3 (weighted EMD + CE, 2 dependent all-reduces per call)": class_leg(synth.segmenter_batch, pcl.EarthMoverDistance(EPS, ITERS, num_classes=5)),
+        "chamfer_loss (ChamferDistance, 1 all-reduce per call)": class_leg(lambda b, n, seed, regime: tuple(x[:, :, :3].contiguous() for x in synth.table_clouds(b, n, seed=seed, regime=regime)), pcl.ChamferDistance()),
+        "path": "pointcloud_b200.ShardedLoss(loss class) forward + backward per step, device-resident inputs, python autograd"}
+
+    # ---- parity of the timed step against the oracle; the reference's own step on the same GPU; the CPU baseline ----
+    reference_gpu, cb, parity_ok, parity = None, None, None, None
     if rank == 0:
+        parity_ok, parity = parity_check(torch, np, pcl, pool, device)
         try:
-            from oracle import build_ref
-            ref = build_ref.load_ref()
-            if ref is not None:
-                sys.path.insert(0, os.path.join(ROOT, "tests"))
-                from helpers import ref_emd_forward
-                ts = []
-                for i in range(6):
-                    p, t, _ = pool[i]
-                    a, b_ = ev(), ev()
-                    a.record(); ref_emd_forward(ref, p, t, EPS, ITERS); b_.record()
-                    torch.cuda.synchronize()
-                    if i >= 2:
-                        ts.append(a.elapsed_time(b_))
-                reference_gpu = {"emd_fwd_ms": statistics.mean(ts), "ours_emd_fwd_ms": emd_ms,
-                                 "what": "unmodified reference emd extension (oracle/_ref/emd.so, 351 launches) on the same B200, same inputs"}
+            reference_gpu = reference_gpu_step(torch, pool, ev, emd_ms)
         except Exception as ex:  # the reference build is optional context
             reference_gpu = {"unavailable": repr(ex)}
         if world == 1 and not args.no_cpu_baseline:
@@ -461,13 +581,16 @@ def main():
             cb = {k: cb[k] for k in ("value", "unit", "cores", "kind", "sample")}
 
     if rank == 0:
+        par = (f"batch-sharded x{world}: {B_PER_GPU} clouds per rank, one NCCL all-reduce (SUM, 4 x fp32 batch sums) per step inside the timed region"
+               if world > 1 else "1 rank (the sharded step degenerates to the local call: no collective)")
         line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": K, "warmup": W, "ms_per_step": ms_per_step,
                 "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
                 "config": {"workload": WORKLOAD, "clouds_per_gpu": B_PER_GPU, "points": NPTS, "eps": EPS, "iters": ITERS,
-                           "chamfer_mode": "unfused", "parallelism": f"batch-sharded x{world}, no data-path collective",
+                           "chamfer_mode": "unfused", "parallelism": par,
                            "l2": f"inputs rotate through {n_sets} sets = {n_sets * 2 * B_PER_GPU * NPTS * 12 / 1e6:.0f} MB > 126 MB L2 (no flush needed)"},
-                "clocks": clocks, "e2e": e2e, "gpu_launches": DeviceStep.KERNELS_PER_STEP * K, "roofline": roofline,
-                "roofline_chamfer": roofline_chamfer,
+                "clocks": clocks, "e2e": e2e, "gpu_launches": KERNELS_PER_STEP * K, "roofline": roofline,
+                "roofline_chamfer": roofline_chamfer, "roofline_bwd": roofline_bwd, "parity_checked": parity_ok, "parity": parity,
+                "sharded_equals_single_gpu": sharded_equals_single, "strong_scaling": strong, "sharded_api": sharded_api,
                 "cpu_baseline": cb, "breakdown_ms": breakdown, "reference_gpu": reference_gpu, "impl": "ours"}
         print(json.dumps(line))
     if world > 1:

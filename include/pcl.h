@@ -69,7 +69,8 @@ PCL_API int pcl_device_info(int *sm_count, int *cc_major, int *cc_minor, int *ma
  * on exact ties, padded rows ignored, then point mean and batch mean.
  *   x (B,P1,D), y (B,P2,D); x_len / y_len: nullable int64[B] (entries in [0,P]); 1 <= D <= 8.
  *   dist_x,idx_x: (B,P1)  dist_y,idx_y: (B,P2)   (padded rows: 0 / 0)
- *   loss_xy[2] = { sum_n mean_i dist_x / max(B,1), same for y }   (loss = loss_xy[0]+loss_xy[1])
+ *   loss_xy[4] = { sum_n mean_i dist_x / max(B,1), same for y,  sum_n mean_i dist_x, same for y }
+ *   (loss = loss_xy[0]+loss_xy[1]; [2..3] are the un-normalised batch sums a batch-sharded caller all-reduces)
  */
 PCL_API size_t pcl_chamfer_workspace_bytes(int B, int P1, int P2);
 PCL_API int pcl_chamfer_fwd(const void *x, int x_dtype, int64_t x_bs, int64_t x_rs, const int64_t *x_len,
@@ -112,6 +113,22 @@ PCL_API int pcl_emd_fwd(const void *xyz1, int dtype1, int64_t bs1, int64_t rs1,
                 int B, int N, float eps, int iters,
                 float *dist, int32_t *assignment, int32_t *stats,
                 void *workspace, size_t workspace_bytes, void *stream);
+/*
+ * pcl_emd_fwd with the loss epilogue of the UNWEIGHTED EarthMoverDistance fused into the same kernel (utils.py:304 with
+ * weights == 1 -- the Autoencoder loss, train.py:82 -- followed by emdFunction.backward, emd_module.py:63-72):
+ *   sums (nullable, device float[3]) = { sum_{b,j} sqrt(dist), B*N, their ratio = the reference's point_l };
+ *   grad_xyz1 (nullable, (B,N,3) fp32) = grad_scale * d(sum sqrt(dist)) / d xyz1
+ *             = 2 * (grad_scale / (2*sqrt(dist))) * (xyz1 - xyz2[assignment])   (torch's sqrt backward, then emd_cuda.cu:284-300),
+ *   so grad_scale = upstream gradient / (B_global*N) yields the final gradient of the loss and no backward kernel is left.
+ * The sum is formed in fp64 in a fixed order (per-CTA partials + last-CTA ticket inside `workspace`, which is then
+ * required: >= pcl_emd_workspace_bytes(B, N)); dist == 0 gives inf/nan exactly like the reference's dists.sqrt().
+ */
+PCL_API int pcl_emd_fwd_fused(const void *xyz1, int dtype1, int64_t bs1, int64_t rs1,
+                      const void *xyz2, int dtype2, int64_t bs2, int64_t rs2,
+                      int B, int N, float eps, int iters,
+                      float *dist, int32_t *assignment, int32_t *stats,
+                      float grad_scale, float *grad_xyz1, float *sums,
+                      void *workspace, size_t workspace_bytes, void *stream);
 /*
  * Replaces emd.backward (emd.cpp:20-23 -> NmDistanceGradKernel, emd_cuda.cu:284-316):
  *   grad_xyz1[j] = (2*graddist[j]) * (xyz1[j] - xyz2[assignment[j]]);  the target gets no gradient
@@ -214,10 +231,13 @@ PCL_API int pcl_ball_query(const void *xyz, int dtype, int64_t bs, int64_t rs,
 /* ------------------------------------------------------------------ composite step ------------------------ */
 /*
  * One pass of the whole hot path over a batch that is already on the device: Chamfer fwd+bwd (upstream gradient 1)
- * and EMD fwd + sqrt-mean (utils.py:304, weights == 1) + bwd.  Chamfer is forked onto a library-owned side stream and
- * runs next to the auction kernel (which leaves 20 of the 148 SMs and about half of the issue slots free); it is joined
- * back into `stream` before the call's work completes.  losses: device float[3] = {chamfer_x, chamfer_y, EMD mean};
- * grad_pred_chamfer / grad_pred_emd: device (B,N,3) fp32.
+ * and EMD fwd + sqrt-mean (utils.py:304, weights == 1) + bwd -- three kernels: the auction with its fused epilogue
+ * (pcl_emd_fwd_fused), the Chamfer forward and the Chamfer backward.  Chamfer is forked onto a library-owned side stream
+ * and runs next to the auction kernel (which leaves 20 of the 148 SMs free); it is joined back into `stream` before the
+ * call's work completes.  losses: device float[8] = {chamfer_x, chamfer_y (batch means), chamfer_x, chamfer_y (batch sums),
+ * sum sqrt(dist), B*N, EMD mean = [4]/[5], unused} -- a batch-sharded caller all-reduces the contiguous [2..5];
+ * grad_pred_chamfer / grad_pred_emd: device (B,N,3) fp32 (d loss / d pred with the batch-mean denominators of THIS batch:
+ * B for Chamfer, B*N for EMD).
  */
 PCL_API size_t pcl_chamfer_emd_step_scratch_bytes(int B, int N);
 PCL_API int pcl_chamfer_emd_step(const void *pred, int dtype1, int64_t bs1, int64_t rs1,
@@ -237,7 +257,7 @@ PCL_API int pcl_chamfer_emd_step(const void *pred, int dtype1, int64_t bs1, int6
 PCL_API size_t pcl_loss_host_scratch_bytes(int B, int N);
 PCL_API int pcl_chamfer_emd_step_host(const float *pred_host, const float *target_host, int B, int N,
                               float eps, int iters, int chamfer_mode,
-                              float *loss_host /* 3: chamfer loss_x, chamfer loss_y, EMD mean sqrt(dist) */,
+                              float *loss_host /* 8: the `losses` vector of pcl_chamfer_emd_step ([0]+[1] = Chamfer loss, [6] = EMD mean sqrt(dist)) */,
                               float *grad_pred_chamfer_host /* nullable B*N*3 */,
                               float *grad_pred_emd_host /* nullable B*N*3 */,
                               void *dev_scratch, size_t dev_scratch_bytes, void *stream);

@@ -11,11 +11,11 @@ from .emd_module import emdFunction, emdModule, emd_forward_raw
 from .losses import (ChamferDistance, EarthMoverDistance, FilterClasses, FilteringChamferDistance,
                      SegmentingChamferDistance)
 from .sampling import farthest_point_sample, query_ball_point, sample_farthest_points
-from .sharded import ShardedLoss, shard_bounds
+from .sharded import ShardedChamferEmdStep, ShardedLoss, shard_bounds
 
 __all__ = [
     "cfg", "chamfer_distance", "chamfer_forward_raw", "emdFunction", "emdModule", "emd_forward_raw",
     "ChamferDistance", "FilteringChamferDistance", "SegmentingChamferDistance", "EarthMoverDistance",
-    "FilterClasses", "ShardedLoss", "shard_bounds",
+    "FilterClasses", "ShardedLoss", "ShardedChamferEmdStep", "shard_bounds",
     "farthest_point_sample", "sample_farthest_points", "query_ball_point",
 ]

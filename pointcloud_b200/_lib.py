@@ -30,6 +30,7 @@ _SIGNATURES = {
     "pcl_emd_max_points": (c_int, []),
     "pcl_emd_workspace_bytes": (c_size_t, [c_int, c_int]),
     "pcl_emd_fwd": (c_int, _PTS + _PTS + [c_int, c_int, c_float, c_int] + [c_void_p] * 3 + [c_void_p, c_size_t, c_void_p]),
+    "pcl_emd_fwd_fused": (c_int, _PTS + _PTS + [c_int, c_int, c_float, c_int] + [c_void_p] * 3 + [c_float, c_void_p, c_void_p] + [c_void_p, c_size_t, c_void_p]),
     "pcl_emd_bwd": (c_int, _PTS + _PTS + [c_int, c_int] + [c_void_p] * 3 + [c_void_p]),
     "pcl_emd_match_hist": (c_int, _PTS + [c_void_p, c_int, c_int, c_int, c_void_p, c_void_p, c_void_p]),
     "pcl_emd_weighted_reduce": (c_int, [c_void_p] * 3 + [c_int] * 3 + [c_void_p, c_void_p, c_size_t, c_void_p]),
@@ -76,13 +77,40 @@ def check(rc: int, what: str):
         raise PclError(f"{what} failed (code {rc}): {lib().pcl_last_error().decode()}")
 
 
+_HAVE_CUDA = None
+
+
 def require_cuda():
-    if not torch.cuda.is_available():
+    global _HAVE_CUDA
+    if _HAVE_CUDA is None:
+        _HAVE_CUDA = bool(torch.cuda.is_available())
+    if not _HAVE_CUDA:
         raise PclError("pointcloud_b200 needs a CUDA device (B200, sm_100a); there is no CPU fallback")
 
 
-def stream_ptr() -> int:
-    return torch.cuda.current_stream().cuda_stream
+def stream_ptr(device=None) -> int:
+    """Raw cudaStream_t of torch's current stream on `device` (default: the current device) -- the C-level accessor, a
+    fraction of a microsecond, where torch.cuda.current_stream().cuda_stream builds a Stream object (~20 us)."""
+    idx = device.index if (device is not None and device.index is not None) else torch.cuda.current_device()
+    return torch._C._cuda_getCurrentRawStream(idx)
+
+
+class _NoGuard:
+    def __enter__(self):
+        return None
+
+    def __exit__(self, *a):
+        return False
+
+
+_NO_GUARD = _NoGuard()
+
+
+def on_device(device):
+    """Device guard that costs nothing when `device` already is the current device (the one-rank-one-device case)."""
+    if device.index is None or device.index == torch.cuda.current_device():
+        return _NO_GUARD
+    return torch.cuda.device(device)
 
 
 def pts_args(t: torch.Tensor):

@@ -23,7 +23,7 @@ def _lengths(lengths, b, p, dev, name):
 
 
 def chamfer_forward_raw(x, y, x_lengths=None, y_lengths=None, mode=None):
-    """One pcl_chamfer_fwd call.  Returns dict(loss_xy (2,), dist_x, idx_x, dist_y, idx_y)."""
+    """One pcl_chamfer_fwd call.  Returns dict(loss_xy (2,) batch means, loss_sums (2,) batch sums, dist_x, idx_x, dist_y, idx_y)."""
     _lib.require_cuda()
     L = _lib.lib()
     x, y = _lib.as_points(x), _lib.as_points(y)
@@ -36,17 +36,17 @@ def chamfer_forward_raw(x, y, x_lengths=None, y_lengths=None, mode=None):
     dev = x.device
     mode = _MODES[cfg.chamfer_mode if mode is None else mode]
     xl, yl = _lengths(x_lengths, b, p1, dev, "x_lengths"), _lengths(y_lengths, b, p2, dev, "y_lengths")
-    with torch.cuda.device(dev):
+    with _lib.on_device(dev):
         dist_x = torch.empty(b, p1, device=dev, dtype=torch.float32); idx_x = torch.empty(b, p1, device=dev, dtype=torch.int32)
         dist_y = torch.empty(b, p2, device=dev, dtype=torch.float32); idx_y = torch.empty(b, p2, device=dev, dtype=torch.int32)
-        loss_xy = torch.empty(2, device=dev, dtype=torch.float32)
+        loss4 = torch.empty(4, device=dev, dtype=torch.float32)
         wsb = L.pcl_chamfer_workspace_bytes(b, p1, p2)
         ws = torch.empty(wsb, device=dev, dtype=torch.uint8)
         rc = L.pcl_chamfer_fwd(*_lib.pts_args(x), _lib.ptr(xl), *_lib.pts_args(y), _lib.ptr(yl), b, p1, p2, d, mode,
                                dist_x.data_ptr(), idx_x.data_ptr(), dist_y.data_ptr(), idx_y.data_ptr(),
-                               loss_xy.data_ptr(), ws.data_ptr(), wsb, _lib.stream_ptr())
+                               loss4.data_ptr(), ws.data_ptr(), wsb, _lib.stream_ptr(dev))
         _lib.check(rc, "pcl_chamfer_fwd")
-    return dict(loss_xy=loss_xy, dist_x=dist_x, idx_x=idx_x, dist_y=dist_y, idx_y=idx_y, x=x, y=y, x_len=xl, y_len=yl)
+    return dict(loss_xy=loss4[:2], loss_sums=loss4[2:], dist_x=dist_x, idx_x=idx_x, dist_y=dist_y, idx_y=idx_y, x=x, y=y, x_len=xl, y_len=yl)
 
 
 class _ChamferFunction(Function):
@@ -67,13 +67,13 @@ class _ChamferFunction(Function):
         p2 = y.shape[1]
         dev = x.device
         grad_xy = grad_xy.contiguous().float()
-        with torch.cuda.device(dev):
+        with _lib.on_device(dev):
             gx = torch.empty(b, p1, d, device=dev, dtype=torch.float32)
             gy = torch.empty(b, p2, d, device=dev, dtype=torch.float32)
             g = grad_xy  # (2,): upstream gradients of loss_x and loss_y, read on the device
             rc = L.pcl_chamfer_bwd(*_lib.pts_args(x), _lib.ptr(xl), *_lib.pts_args(y), _lib.ptr(yl), b, p1, p2, d,
                                    idx_x.data_ptr(), idx_y.data_ptr(), g.data_ptr(), gx.data_ptr(), gy.data_ptr(),
-                                   _lib.stream_ptr())
+                                   _lib.stream_ptr(dev))
             _lib.check(rc, "pcl_chamfer_bwd")
         dtx, devx, dty, devy = ctx.in_meta
         return gx.to(device=devx, dtype=dtx), gy.to(device=devy, dtype=dty), None, None, None

@@ -43,11 +43,6 @@ int device_info(DeviceInfo *out) {
     return PCL_OK;
 }
 
-namespace {
-__global__ void fill2_kernel(float *p, float v) { p[0] = v; p[1] = v; }
-__global__ void emd_mean_kernel(const float *sums, float *out) { *out = sums[0] / sums[1]; }
-}  // namespace
-
 }  // namespace pcl
 
 using namespace pcl;
@@ -78,7 +73,7 @@ StepLayout step_layout(int B, int N) {
     L.dist_x = o; o += per; L.idx_x = o; o += per; L.dist_y = o; o += per; L.idx_y = o; o += per;
     L.grad_y = o; o += pts;
     L.emd_dist = o; o += per; L.emd_asg = o; o += per;
-    L.scalars = o; o += 256;  // [0..1] emd sums, [2..3] ones
+    L.scalars = o; o += 256;  // reserved
     L.ch_ws = o; o += pcl_chamfer_workspace_bytes(B, N, N);
     L.emd_ws = o; o += pcl_emd_workspace_bytes(B, N);
     L.total = o;
@@ -139,33 +134,23 @@ extern "C" int pcl_chamfer_emd_step(const void *pred, int dtype1, int64_t bs1, i
     int rc = side_stream(&ss);
     if (rc) return rc;
     unsigned char *d = (unsigned char *)scratch;
-    float *sc = (float *)(d + L.scalars);
-    fill2_kernel<<<1, 1, 0, st>>>(sc + 2, 1.0f);
     PCL_CUDA(cudaEventRecord(ss->fork, st));
     PCL_CUDA(cudaStreamWaitEvent(ss->side, ss->fork, 0));
-    // caller's stream first: the auction kernel takes its 128 SMs (one 512-thread CTA each) right away ...
-    rc = pcl_emd_fwd(pred, dtype1, bs1, rs1, target, dtype2, bs2, rs2, B, N, eps, iters, (float *)(d + L.emd_dist),
-                     (int32_t *)(d + L.emd_asg), nullptr, d + L.emd_ws, pcl_emd_workspace_bytes(B, N), stream);
+    // caller's stream: ONE kernel for the whole EMD side -- auction, CalcDist, sqrt-mean (utils.py:304 with weights == 1) and the
+    // gradient of that mean (emd_module.py:63-72), losses[4..6] = {sum sqrt(dist), B*N, mean}.  It takes its 128 SMs right away ...
+    rc = pcl_emd_fwd_fused(pred, dtype1, bs1, rs1, target, dtype2, bs2, rs2, B, N, eps, iters, (float *)(d + L.emd_dist),
+                           (int32_t *)(d + L.emd_asg), nullptr, 1.0f / ((float)B * (float)N), grad_pred_emd, losses + 4, d + L.emd_ws,
+                           pcl_emd_workspace_bytes(B, N), stream);
     if (rc) return rc;
-    // ... then the side stream: Chamfer forward + backward (upstream gradient 1) fill the remaining SMs and the spare
-    // registers / shared memory / issue slots next to the auction CTAs
+    // ... then the side stream: Chamfer forward + backward (upstream gradient 1) fill the remaining SMs
     rc = pcl_chamfer_fwd(pred, dtype1, bs1, rs1, nullptr, target, dtype2, bs2, rs2, nullptr, B, N, N, 3, chamfer_mode,
                          (float *)(d + L.dist_x), (int32_t *)(d + L.idx_x), (float *)(d + L.dist_y), (int32_t *)(d + L.idx_y),
                          losses, d + L.ch_ws, pcl_chamfer_workspace_bytes(B, N, N), ss->side);
     if (rc) return rc;
-    rc = pcl_chamfer_bwd(pred, dtype1, bs1, rs1, nullptr, target, dtype2, bs2, rs2, nullptr, B, N, N, 3, (int32_t *)(d + L.idx_x),
-                         (int32_t *)(d + L.idx_y), sc + 2, grad_pred_chamfer, (float *)(d + L.grad_y), ss->side);
+    rc = chamfer_bwd_impl(pred, dtype1, bs1, rs1, nullptr, target, dtype2, bs2, rs2, nullptr, B, N, N, 3, (int32_t *)(d + L.idx_x),
+                          (int32_t *)(d + L.idx_y), nullptr, 1.f, 1.f, grad_pred_chamfer, (float *)(d + L.grad_y), ss->side);
     if (rc) return rc;
     PCL_CUDA(cudaEventRecord(ss->join, ss->side));
-    // caller's stream: mean sqrt(dist) (utils.py:304 with weights == 1) and the EMD backward
-    rc = pcl_emd_weighted_reduce((float *)(d + L.emd_dist), nullptr, nullptr, B, N, 0, sc + 0, d + L.emd_ws,
-                                 pcl_emd_workspace_bytes(B, N), stream);
-    if (rc) return rc;
-    rc = pcl_emd_weighted_bwd(pred, dtype1, bs1, rs1, target, dtype2, bs2, rs2, B, N, (int32_t *)(d + L.emd_asg),
-                              (float *)(d + L.emd_dist), nullptr, nullptr, 0, sc + 0, sc + 2, grad_pred_emd, stream);
-    if (rc) return rc;
-    emd_mean_kernel<<<1, 1, 0, st>>>(sc + 0, losses + 2);
-    PCL_CUDA(cudaGetLastError());
     PCL_CUDA(cudaStreamWaitEvent(st, ss->join, 0));
     return PCL_OK;
 }
@@ -193,8 +178,8 @@ extern "C" int pcl_chamfer_emd_step_host(const float *pred_host, const float *ta
     int rc = pcl_chamfer_emd_step(pred, PCL_F32, bs, rs, target, PCL_F32, bs, rs, B, N, eps, iters, chamfer_mode, losses,
                                   (float *)(d + L.grad_x), (float *)(d + L.grad_emd), d + L.step, step_layout(B, N).total, stream);
     if (rc) return rc;
-    // results back to the host: {chamfer_x, chamfer_y, EMD mean}
-    PCL_CUDA(cudaMemcpyAsync(loss_host, losses, 3 * sizeof(float), cudaMemcpyDeviceToHost, st));
+    // results back to the host: the 8-float `losses` vector of pcl_chamfer_emd_step
+    PCL_CUDA(cudaMemcpyAsync(loss_host, losses, 8 * sizeof(float), cudaMemcpyDeviceToHost, st));
     if (grad_pred_chamfer_host) PCL_CUDA(cudaMemcpyAsync(grad_pred_chamfer_host, d + L.grad_x, bytes, cudaMemcpyDeviceToHost, st));
     if (grad_pred_emd_host) PCL_CUDA(cudaMemcpyAsync(grad_pred_emd_host, d + L.grad_emd, bytes, cudaMemcpyDeviceToHost, st));
     return PCL_OK;

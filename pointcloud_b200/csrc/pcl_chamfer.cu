@@ -53,6 +53,13 @@ __device__ __forceinline__ float hi2(u64 v) { return __uint_as_float((unsigned)(
 __device__ __forceinline__ u64 ffma2(u64 a, u64 b, u64 c) { u64 r; asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(r) : "l"(a), "l"(b), "l"(c)); return r; }
 __device__ __forceinline__ float fmin3(float a, float b, float c) { float r; asm("min.f32 %0, %1, %2, %3;" : "=f"(r) : "f"(a), "f"(b), "f"(c)); return r; }  // NaN operands are ignored
 
+template <bool FMA>
+__device__ __forceinline__ float sqdist3(float qx, float qy, float qz, const float4 &t) {
+    const float dx = __fsub_rn(qx, t.x), dy = __fsub_rn(qy, t.y), dz = __fsub_rn(qz, t.z);
+    if constexpr (FMA) return __fmaf_rn(dz, dz, __fmaf_rn(dy, dy, __fmul_rn(dx, dx)));
+    else return __fadd_rn(__fadd_rn(__fmul_rn(dx, dx), __fmul_rn(dy, dy)), __fmul_rn(dz, dz));
+}
+
 // length of cloud n, clamped to [0, P]: pytorch3d raises on lengths > P; a kernel cannot, but it must not read past the cloud
 __device__ __forceinline__ int len_of(const int64_t *len, int n, int P) {
     if (!len) return P;
@@ -60,11 +67,39 @@ __device__ __forceinline__ int len_of(const int64_t *len, int n, int P) {
     return (int)(v < 0 ? 0 : (v > P ? P : v));
 }
 
-template <bool FMA>
-__device__ __forceinline__ float sqdist3(float qx, float qy, float qz, const float4 &t) {
-    const float dx = __fsub_rn(qx, t.x), dy = __fsub_rn(qy, t.y), dz = __fsub_rn(qz, t.z);
-    if constexpr (FMA) return __fmaf_rn(dz, dz, __fmaf_rn(dy, dy, __fmul_rn(dx, dx)));
-    else return __fadd_rn(__fadd_rn(__fmul_rn(dx, dx), __fmul_rn(dy, dy)), __fmul_rn(dz, dz));
+// Tail of both forward kernels: the CTA's partial sum goes to the workspace; the CTA that takes the LAST ticket of the grid
+// (zeroed by the host call) then forms  loss_xy[dir] = sum_n (sum_i dist / clamp(len,1)) / max(B,1)  from all partials in a
+// fixed order (deterministic scalar, fp64) -- no memset of the partials and no second launch.  Needs >= 64 threads per CTA.
+__device__ __forceinline__ void finish_block(float s /* valid on thread 0 */, float *__restrict__ partial, int nblk, int dir, int n,
+                                             unsigned *__restrict__ ticket, int P1, int P2, const int64_t *__restrict__ x_len,
+                                             const int64_t *__restrict__ y_len, float *__restrict__ loss_xy) {
+    __shared__ int last_flag;
+    const int B = (int)gridDim.y;
+    if (threadIdx.x == 0) {
+        partial[((size_t)dir * B + n) * nblk + blockIdx.x] = s;
+        __threadfence();
+        last_flag = (atomicAdd(ticket, 1u) == gridDim.x * gridDim.y * gridDim.z - 1) ? 1 : 0;
+    }
+    __syncthreads();
+    if (!last_flag || threadIdx.x >= 64) return;
+    __threadfence();
+    __shared__ double acc[2][32];
+    const int d = threadIdx.x >> 5, lane = threadIdx.x & 31;  // one warp per direction
+    double a = 0.0;
+    for (int c = lane; c < B; c += 32) {
+        double t = 0.0;
+        for (int k = 0; k < (int)gridDim.x; k++) t += (double)__ldcg(&partial[((size_t)d * B + c) * nblk + k]);
+        const int len = d ? len_of(y_len, c, P2) : len_of(x_len, c, P1);
+        a += t / (double)(len > 1 ? len : 1);
+    }
+    acc[d][lane] = a;
+    __syncwarp();
+    if (lane == 0) {
+        double t = 0.0;
+        for (int k = 0; k < 32; k++) t += acc[d][k];
+        loss_xy[d] = (float)(t / (double)(B > 1 ? B : 1));
+        loss_xy[2 + d] = (float)t;  // the un-normalised batch sum: what a batch-sharded caller all-reduces
+    }
 }
 
 template <int NWARPS>
@@ -135,7 +170,8 @@ template <bool FMA>
 __global__ void __launch_bounds__(C3_THREADS, PCL_C3_MINB)
 chamfer_nn3_kernel(Pts x, const int64_t *__restrict__ x_len, Pts y, const int64_t *__restrict__ y_len, int P1, int P2,
                    float *__restrict__ dist_x, int *__restrict__ idx_x, float *__restrict__ dist_y,
-                   int *__restrict__ idx_y, float *__restrict__ partial, int nblk) {
+                   int *__restrict__ idx_y, float *__restrict__ partial, int nblk, unsigned *__restrict__ ticket,
+                   float *__restrict__ loss_xy) {
     __shared__ float4 tA[C3_TILE / 2 + C3_GROUP];  // per pair of targets {x0, x1, y0, y1} (+ slack for the read-ahead)
     __shared__ float4 tB[C3_TILE / 2 + C3_GROUP];  //                     {z0, z1, |t0|^2, |t1|^2}
     constexpr int C3_PPT = C3_TILE / C3_THREADS;   // staged points per thread and tile
@@ -146,7 +182,10 @@ chamfer_nn3_kernel(Pts x, const int64_t *__restrict__ x_len, Pts y, const int64_
     const Pts q = dir ? y : x, t = dir ? x : y;
     const int PQ = dir ? P2 : P1;
     const int q0 = blockIdx.x * C3_QUERIES;
-    if (q0 >= PQ) return;  // block-uniform
+    if (q0 >= PQ) {  // block-uniform: beyond the shorter cloud -- contributes a zero partial (and may be the last CTA)
+        finish_block(0.f, partial, nblk, dir, n, ticket, P1, P2, x_len, y_len, loss_xy);
+        return;
+    }
     const int lq = dir ? len_of(y_len, n, P2) : len_of(x_len, n, P1);
     const int lt = dir ? len_of(x_len, n, P1) : len_of(y_len, n, P2);
     float *dist = (dir ? dist_y : dist_x) + (size_t)n * PQ;
@@ -302,7 +341,7 @@ chamfer_nn3_kernel(Pts x, const int64_t *__restrict__ x_len, Pts y, const int64_
         }
     }
     s = block_sum<C3_THREADS / 32>(s, red);
-    if (threadIdx.x == 0) partial[((size_t)dir * gridDim.y + n) * nblk + blockIdx.x] = s;
+    finish_block(s, partial, nblk, dir, n, ticket, P1, P2, x_len, y_len, loss_xy);
 }
 
 // Generic feature width (ChamferDistance over all channels, utils.py:209-211).  One query per thread.
@@ -310,7 +349,8 @@ template <bool FMA, int D>
 __global__ void __launch_bounds__(CH_THREADS)
 chamfer_nnD_kernel(Pts x, const int64_t *__restrict__ x_len, Pts y, const int64_t *__restrict__ y_len, int P1, int P2,
                    float *__restrict__ dist_x, int *__restrict__ idx_x, float *__restrict__ dist_y,
-                   int *__restrict__ idx_y, float *__restrict__ partial, int nblk) {
+                   int *__restrict__ idx_y, float *__restrict__ partial, int nblk, unsigned *__restrict__ ticket,
+                   float *__restrict__ loss_xy) {
     constexpr int TILE = 512;
     __shared__ float tile[TILE * D];
     __shared__ float red[4];
@@ -318,7 +358,10 @@ chamfer_nnD_kernel(Pts x, const int64_t *__restrict__ x_len, Pts y, const int64_
     const Pts q = dir ? y : x, t = dir ? x : y;
     const int PQ = dir ? P2 : P1;
     const int q0 = blockIdx.x * CH_THREADS;
-    if (q0 >= PQ) return;
+    if (q0 >= PQ) {
+        finish_block(0.f, partial, nblk, dir, n, ticket, P1, P2, x_len, y_len, loss_xy);
+        return;
+    }
     const int lq = dir ? len_of(y_len, n, P2) : len_of(x_len, n, P1);
     const int lt = dir ? len_of(x_len, n, P1) : len_of(y_len, n, P2);
     float *dist = (dir ? dist_y : dist_x) + (size_t)n * PQ;
@@ -358,30 +401,7 @@ chamfer_nnD_kernel(Pts x, const int64_t *__restrict__ x_len, Pts y, const int64_
         dist[i] = s; idx[i] = valid ? bi : 0;
     }
     s = block_sum<4>(s, red);
-    if (threadIdx.x == 0) partial[((size_t)dir * gridDim.y + n) * nblk + blockIdx.x] = s;
-}
-
-// loss_xy[dir] = sum_n (sum_i dist / clamp(len,1)) / max(B,1); fixed summation order => deterministic.
-__global__ void chamfer_finish_kernel(const float *__restrict__ partial, int B, int nblk, int nbx, int nby, int P1, int P2,
-                                      const int64_t *__restrict__ x_len, const int64_t *__restrict__ y_len,
-                                      float *__restrict__ loss_xy) {
-    __shared__ double acc[2][32];
-    const int dir = threadIdx.x >> 5, lane = threadIdx.x & 31;  // 64 threads: one warp per direction
-    double a = 0.0;
-    for (int n = lane; n < B; n += 32) {
-        const int used = dir ? nby : nbx;
-        double s = 0.0;
-        for (int k = 0; k < used; k++) s += (double)partial[((size_t)dir * B + n) * nblk + k];
-        const int64_t len = dir ? len_of(y_len, n, P2) : len_of(x_len, n, P1);
-        a += s / (double)(len > 1 ? len : 1);
-    }
-    acc[dir][lane] = a;
-    __syncwarp();
-    if (lane == 0) {
-        double s = 0.0;
-        for (int k = 0; k < 32; k++) s += acc[dir][k];
-        loss_xy[dir] = (float)(s / (double)(B > 1 ? B : 1));
-    }
+    finish_block(s, partial, nblk, dir, n, ticket, P1, P2, x_len, y_len, loss_xy);
 }
 
 // Backward: grid (ceil(maxP/256), B, 2).  All contributions go through fp32 red.global.add onto
@@ -389,7 +409,8 @@ __global__ void chamfer_finish_kernel(const float *__restrict__ partial, int B, 
 __global__ void __launch_bounds__(256)
 chamfer_bwd_kernel(Pts x, const int64_t *__restrict__ x_len, Pts y, const int64_t *__restrict__ y_len, int B, int P1,
                    int P2, int D, const int *__restrict__ idx_x, const int *__restrict__ idx_y,
-                   const float *__restrict__ grad_out, float *__restrict__ grad_x, float *__restrict__ grad_y) {
+                   const float *__restrict__ grad_out, float g_imm_x, float g_imm_y, float *__restrict__ grad_x,
+                   float *__restrict__ grad_y) {
     const int dir = blockIdx.z, n = blockIdx.y;
     const int i = blockIdx.x * blockDim.x + threadIdx.x;
     const Pts q = dir ? y : x, t = dir ? x : y;
@@ -397,7 +418,7 @@ chamfer_bwd_kernel(Pts x, const int64_t *__restrict__ x_len, Pts y, const int64_
     const int lq = dir ? len_of(y_len, n, P2) : len_of(x_len, n, P1);
     const int lt = dir ? len_of(x_len, n, P1) : len_of(y_len, n, P2);
     if (i >= lq || lt <= 0) return;
-    const float g = __ldg(grad_out + dir);
+    const float g = grad_out ? __ldg(grad_out + dir) : (dir ? g_imm_y : g_imm_x);  // upstream gradient: device scalar or immediate
     const float gd = g / (float)(B > 1 ? B : 1) / (float)(lq > 1 ? lq : 1);
     const int j = (dir ? idx_y : idx_x)[(size_t)n * PQ + i];
     float *gq = (dir ? grad_y : grad_x) + ((size_t)n * PQ + i) * D;
@@ -412,17 +433,16 @@ chamfer_bwd_kernel(Pts x, const int64_t *__restrict__ x_len, Pts y, const int64_
 
 template <bool FMA>
 int launch_fwd(const Pts &x, const int64_t *x_len, const Pts &y, const int64_t *y_len, int B, int P1, int P2, int D,
-               float *dist_x, int *idx_x, float *dist_y, int *idx_y, float *partial, int nblk, int sm_count,
+               float *dist_x, int *idx_x, float *dist_y, int *idx_y, float *partial, int nblk, unsigned *ticket, float *loss_xy,
                cudaStream_t st) {
     const int maxP = P1 > P2 ? P1 : P2;
     if (D == 3) {
         dim3 grid((maxP + C3_QUERIES - 1) / C3_QUERIES, B, 2);
-        chamfer_nn3_kernel<FMA><<<grid, C3_THREADS, 0, st>>>(x, x_len, y, y_len, P1, P2, dist_x, idx_x, dist_y, idx_y, partial, nblk);
-        (void)sm_count;
+        chamfer_nn3_kernel<FMA><<<grid, C3_THREADS, 0, st>>>(x, x_len, y, y_len, P1, P2, dist_x, idx_x, dist_y, idx_y, partial, nblk, ticket, loss_xy);
     } else {
         dim3 grid((maxP + CH_THREADS - 1) / CH_THREADS, B, 2);
 #define PCL_LAUNCH_NND(DD) \
-    case DD: chamfer_nnD_kernel<FMA, DD><<<grid, CH_THREADS, 0, st>>>(x, x_len, y, y_len, P1, P2, dist_x, idx_x, dist_y, idx_y, partial, nblk); break
+    case DD: chamfer_nnD_kernel<FMA, DD><<<grid, CH_THREADS, 0, st>>>(x, x_len, y, y_len, P1, P2, dist_x, idx_x, dist_y, idx_y, partial, nblk, ticket, loss_xy); break
         switch (D) {
             PCL_LAUNCH_NND(1); PCL_LAUNCH_NND(2); PCL_LAUNCH_NND(4); PCL_LAUNCH_NND(5);
             PCL_LAUNCH_NND(6); PCL_LAUNCH_NND(7); PCL_LAUNCH_NND(8);
@@ -455,7 +475,7 @@ using namespace pcl;
 
 extern "C" size_t pcl_chamfer_workspace_bytes(int B, int P1, int P2) {
     if (B <= 0) return 256;
-    return align_up((size_t)2 * B * nblk_for(P1, P2) * sizeof(float), 256);
+    return 256 + align_up((size_t)2 * B * nblk_for(P1, P2) * sizeof(float), 256);  // [ticket][per-CTA partial sums]
 }
 
 extern "C" int pcl_chamfer_fwd(const void *x, int x_dtype, int64_t x_bs, int64_t x_rs, const int64_t *x_len,
@@ -476,20 +496,40 @@ extern "C" int pcl_chamfer_fwd(const void *x, int x_dtype, int64_t x_bs, int64_t
     DeviceInfo di;
     if ((rc = device_info(&di))) return rc;
     if (B == 0 || (P1 == 0 && P2 == 0)) {
-        PCL_CUDA(cudaMemsetAsync(loss_xy, 0, 2 * sizeof(float), st));
+        PCL_CUDA(cudaMemsetAsync(loss_xy, 0, 4 * sizeof(float), st));
         return PCL_OK;
     }
     const Pts xp{x, x_bs, x_rs, x_dtype}, yp{y, y_bs, y_rs, y_dtype};
-    float *partial = (float *)workspace;
+    unsigned *ticket = (unsigned *)workspace;
+    float *partial = (float *)((unsigned char *)workspace + 256);
     const int nblk = nblk_for(P1, P2);
-    // blocks that return early (beyond the shorter cloud) must still contribute zeros
-    PCL_CUDA(cudaMemsetAsync(partial, 0, (size_t)2 * B * nblk * sizeof(float), st));
+    PCL_CUDA(cudaMemsetAsync(ticket, 0, sizeof(unsigned), st));  // every CTA writes its partial (zeros beyond the shorter cloud); the last one sums
     rc = (mode == PCL_CHAMFER_FMA)
-             ? launch_fwd<true>(xp, x_len, yp, y_len, B, P1, P2, D, dist_x, idx_x, dist_y, idx_y, partial, nblk, di.sm_count, st)
-             : launch_fwd<false>(xp, x_len, yp, y_len, B, P1, P2, D, dist_x, idx_x, dist_y, idx_y, partial, nblk, di.sm_count, st);
+             ? launch_fwd<true>(xp, x_len, yp, y_len, B, P1, P2, D, dist_x, idx_x, dist_y, idx_y, partial, nblk, ticket, loss_xy, st)
+             : launch_fwd<false>(xp, x_len, yp, y_len, B, P1, P2, D, dist_x, idx_x, dist_y, idx_y, partial, nblk, ticket, loss_xy, st);
     if (rc) return rc;
     PCL_CUDA(cudaGetLastError());
-    chamfer_finish_kernel<<<1, 64, 0, st>>>(partial, B, nblk, nblk, nblk, P1, P2, x_len, y_len, loss_xy);
+    return PCL_OK;
+}
+
+// shared by pcl_chamfer_bwd (upstream gradients on the device) and the composite step (immediate upstream gradients)
+int pcl::chamfer_bwd_impl(const void *x, int x_dtype, int64_t x_bs, int64_t x_rs, const int64_t *x_len, const void *y, int y_dtype,
+                          int64_t y_bs, int64_t y_rs, const int64_t *y_len, int B, int P1, int P2, int D, const int32_t *idx_x,
+                          const int32_t *idx_y, const float *grad_out, float g_imm_x, float g_imm_y, float *grad_x, float *grad_y,
+                          cudaStream_t st) {
+    int rc = check_args(x, x_dtype, y, y_dtype, B, P1, P2, D);
+    if (rc) return rc;
+    if (B > 0 && ((P1 > 0 && (!grad_x || !idx_x)) || (P2 > 0 && (!grad_y || !idx_y)))) {
+        set_error("chamfer_bwd: null argument"); return PCL_E_ARG;
+    }
+    if (B == 0) return PCL_OK;
+    if (P1 > 0) PCL_CUDA(cudaMemsetAsync(grad_x, 0, (size_t)B * P1 * D * sizeof(float), st));
+    if (P2 > 0) PCL_CUDA(cudaMemsetAsync(grad_y, 0, (size_t)B * P2 * D * sizeof(float), st));
+    if (P1 == 0 || P2 == 0) return PCL_OK;
+    const Pts xp{x, x_bs, x_rs, x_dtype}, yp{y, y_bs, y_rs, y_dtype};
+    const int maxP = P1 > P2 ? P1 : P2;
+    dim3 grid((maxP + 255) / 256, B, 2);
+    chamfer_bwd_kernel<<<grid, 256, 0, st>>>(xp, x_len, yp, y_len, B, P1, P2, D, idx_x, idx_y, grad_out, g_imm_x, g_imm_y, grad_x, grad_y);
     PCL_CUDA(cudaGetLastError());
     return PCL_OK;
 }
@@ -498,20 +538,7 @@ extern "C" int pcl_chamfer_bwd(const void *x, int x_dtype, int64_t x_bs, int64_t
                                const void *y, int y_dtype, int64_t y_bs, int64_t y_rs, const int64_t *y_len, int B,
                                int P1, int P2, int D, const int32_t *idx_x, const int32_t *idx_y,
                                const float *grad_out, float *grad_x, float *grad_y, void *stream) {
-    int rc = check_args(x, x_dtype, y, y_dtype, B, P1, P2, D);
-    if (rc) return rc;
-    if (!grad_out || (B > 0 && ((P1 > 0 && (!grad_x || !idx_x)) || (P2 > 0 && (!grad_y || !idx_y))))) {
-        set_error("chamfer_bwd: null argument"); return PCL_E_ARG;
-    }
-    cudaStream_t st = (cudaStream_t)stream;
-    if (B == 0) return PCL_OK;
-    if (P1 > 0) PCL_CUDA(cudaMemsetAsync(grad_x, 0, (size_t)B * P1 * D * sizeof(float), st));
-    if (P2 > 0) PCL_CUDA(cudaMemsetAsync(grad_y, 0, (size_t)B * P2 * D * sizeof(float), st));
-    if (P1 == 0 || P2 == 0) return PCL_OK;
-    const Pts xp{x, x_bs, x_rs, x_dtype}, yp{y, y_bs, y_rs, y_dtype};
-    const int maxP = P1 > P2 ? P1 : P2;
-    dim3 grid((maxP + 255) / 256, B, 2);
-    chamfer_bwd_kernel<<<grid, 256, 0, st>>>(xp, x_len, yp, y_len, B, P1, P2, D, idx_x, idx_y, grad_out, grad_x, grad_y);
-    PCL_CUDA(cudaGetLastError());
-    return PCL_OK;
+    if (!grad_out) { set_error("chamfer_bwd: null argument"); return PCL_E_ARG; }
+    return chamfer_bwd_impl(x, x_dtype, x_bs, x_rs, x_len, y, y_dtype, y_bs, y_rs, y_len, B, P1, P2, D, idx_x, idx_y, grad_out, 0.f, 0.f,
+                            grad_x, grad_y, (cudaStream_t)stream);
 }

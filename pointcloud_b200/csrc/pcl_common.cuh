@@ -55,6 +55,12 @@ __device__ __forceinline__ float3 ld_xyz(const Pts &a, int64_t b, int64_t row) {
     return make_float3(ld_any(a, o), ld_any(a, o + 1), ld_any(a, o + 2));
 }
 
+// Chamfer backward with the upstream gradients either on the device (grad_out != nullptr) or as immediates (pcl_chamfer.cu)
+int chamfer_bwd_impl(const void *x, int x_dtype, int64_t x_bs, int64_t x_rs, const int64_t *x_len, const void *y, int y_dtype,
+                     int64_t y_bs, int64_t y_rs, const int64_t *y_len, int B, int P1, int P2, int D, const int32_t *idx_x,
+                     const int32_t *idx_y, const float *grad_out, float g_imm_x, float g_imm_y, float *grad_x, float *grad_y,
+                     cudaStream_t st);
+
 static inline bool dtype_ok(int dt) { return dt == PCL_F32 || dt == PCL_F16 || dt == PCL_BF16; }
 static inline size_t align_up(size_t v, size_t a) { return (v + a - 1) / a * a; }
 

@@ -266,7 +266,8 @@ __global__ void __launch_bounds__(EMD_THREADS, 1)
 emd_auction_kernel(Pts xyz1, Pts xyz2, int N, float eps, int iters, int flags, int pcap, int wpb_max, int items_target,
                    float *__restrict__ dist,
                    int *__restrict__ assignment, int *__restrict__ stats, long long *__restrict__ prof,
-                   unsigned char *__restrict__ cold_ws) {
+                   unsigned char *__restrict__ cold_ws, float grad_scale, float *__restrict__ grad_xyz1,
+                   double *__restrict__ part, unsigned *__restrict__ ticket, float *__restrict__ sums_out) {
     long long pt[16] = {0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0}, pc = 0, bid0 = 0;
 #define PCL_TICK(i)                                              \
     if constexpr (PROF) {                                        \
@@ -810,18 +811,59 @@ emd_auction_kernel(Pts xyz1, Pts xyz2, int N, float eps, int iters, int flags, i
     }
 
     // ---- CalcDist (emd_cuda.cu:217-226) + outputs in ORIGINAL index order; points split over the cluster ----
+    // Fused loss epilogue of the unweighted EMD (utils.py:304 with weights == 1; emd_module.py:63-72 + emd_cuda.cu:284-300):
+    //   grad_xyz1 = grad_scale * d(sum sqrt(dist)) / d xyz1 = 2 * (grad_scale / (2 sqrt(dist))) * (xyz1 - xyz2[assignment])
+    // in the operation order of torch's sqrt backward followed by NmDistanceGradKernel, and sum sqrt(dist) in fp64.
     __syncthreads();
+    double sq_sum = 0.0;
     for (int jp = rank * T + tid; jp < N; jp += cs * T) {
         const unsigned k = S.asg[jp];
         float d = 0.f;
+        float3 gr = make_float3(0.f, 0.f, 0.f);
         if (k != NONE16) {
             const float3 a = pred_xyz(jp);
             const float4 tp = S.tgt[k];
-            d = sq3_ref(__fsub_rn(a.x, tp.x), __fsub_rn(a.y, tp.y), __fsub_rn(a.z, tp.z));
+            const float dx = __fsub_rn(a.x, tp.x), dy = __fsub_rn(a.y, tp.y), dz = __fsub_rn(a.z, tp.z);
+            d = sq3_ref(dx, dy, dz);
+            if (grad_xyz1) {
+                const float g2 = __fmul_rn(__fdiv_rn(grad_scale, __fmul_rn(2.f, __fsqrt_rn(d))), 2.f);  // d == 0: inf, like the reference
+                gr = make_float3(__fmul_rn(g2, dx), __fmul_rn(g2, dy), __fmul_rn(g2, dz));
+            }
         }
         const int jo = S.pperm ? (int)S.pperm[jp] : jp;
-        dist[(size_t)cloud * N + jo] = d;
-        assignment[(size_t)cloud * N + jo] = (k != NONE16) ? (S.tperm ? (int)S.tperm[k] : (int)k) : -1;
+        const size_t o = (size_t)cloud * N + jo;
+        dist[o] = d;
+        assignment[o] = (k != NONE16) ? (S.tperm ? (int)S.tperm[k] : (int)k) : -1;
+        if (grad_xyz1) { grad_xyz1[o * 3 + 0] = gr.x; grad_xyz1[o * 3 + 1] = gr.y; grad_xyz1[o * 3 + 2] = gr.z; }
+        sq_sum += (double)__fsqrt_rn(d);
+    }
+    if (part) {
+        // per-CTA partial in a fixed order, then the CTA that takes the last ticket adds the partials of the whole grid in
+        // index order: one deterministic scalar without a second launch (the ticket is zeroed by the host call)
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) sq_sum += __shfl_xor_sync(0xffffffffu, sq_sum, o);
+        double *red = reinterpret_cast<double *>(S.pbest);  // the slice-partial buffer is free now (8-byte aligned, >= 2 KB)
+        if (lane == 0) red[wid] = sq_sum;
+        __syncthreads();
+        if (tid == 0) {
+            double b = 0.0;
+            for (int w = 0; w < EMD_WARPS; w++) b += red[w];
+            part[blockIdx.x] = b;
+            __threadfence();
+            S.wsum[41] = (atomicAdd(ticket, 1u) == gridDim.x - 1) ? 1 : 0;
+        }
+        __syncthreads();
+        if (S.wsum[41] && wid == 0) {
+            __threadfence();
+            double b = 0.0;
+            for (int i = lane; i < (int)gridDim.x; i += 32) b += __ldcg(&part[i]);  // lane-strided, then a fixed shuffle tree
+#pragma unroll
+            for (int o = 16; o > 0; o >>= 1) b += __shfl_xor_sync(0xffffffffu, b, o);
+            if (lane == 0) {
+                const float total = (float)b, count = (float)((double)(gridDim.x / cs) * (double)N);
+                sums_out[0] = total; sums_out[1] = count; sums_out[2] = total / count;
+            }
+        }
     }
     PCL_TICK(5)
     if constexpr (PROF) {
@@ -1012,8 +1054,14 @@ using namespace pcl;
 
 extern "C" int pcl_emd_max_points(void) { return EMD_MAX_N; }
 
+// workspace layout: [ticket, 256 B][per-CTA partial sums of the fused epilogue, fp64][the rest: reduction partials of
+// pcl_emd_weighted_reduce | profile counters | cold auction state for large N]
+static size_t emd_fused_bytes(int B) {
+    const size_t ctas = (size_t)(B > 256 ? B : 256);  // grid = B * cs <= max(SM count, B)
+    return 256 + align_up(ctas * sizeof(double), 256);
+}
+
 extern "C" size_t pcl_emd_workspace_bytes(int B, int N) {
-    (void)N;
     const size_t red = (size_t)RED_BLOCKS * 2 * sizeof(double), prof = ((size_t)(B > 0 ? B : 0) * 16 * 16 + 512) * sizeof(long long);
     size_t cold = 0;
     if (N > EMD_SMEM_ONLY_N && B > 0) {  // large clouds: per-CTA global region for the cold state, sized for the largest cluster
@@ -1021,7 +1069,7 @@ extern "C" size_t pcl_emd_workspace_bytes(int B, int N) {
         cold = (size_t)B * cs * ((emd_cold_bytes(N) + 255) / 256 * 256);
     }
     const size_t m = red > prof ? red : prof;
-    return align_up(m > cold ? m : cold, 256);
+    return emd_fused_bytes(B) + align_up(m > cold ? m : cold, 256);
 }
 
 static int emd_check(const void *xyz1, int dtype1, const void *xyz2, int dtype2, int B, int N, const char *who) {
@@ -1035,12 +1083,27 @@ static int emd_check(const void *xyz1, int dtype1, const void *xyz2, int dtype2,
 extern "C" int pcl_emd_fwd(const void *xyz1, int dtype1, int64_t bs1, int64_t rs1, const void *xyz2, int dtype2,
                            int64_t bs2, int64_t rs2, int B, int N, float eps, int iters, float *dist,
                            int32_t *assignment, int32_t *stats, void *workspace, size_t workspace_bytes, void *stream) {
+    return pcl_emd_fwd_fused(xyz1, dtype1, bs1, rs1, xyz2, dtype2, bs2, rs2, B, N, eps, iters, dist, assignment, stats, 0.f, nullptr,
+                             nullptr, workspace, workspace_bytes, stream);
+}
+
+extern "C" int pcl_emd_fwd_fused(const void *xyz1, int dtype1, int64_t bs1, int64_t rs1, const void *xyz2, int dtype2,
+                                 int64_t bs2, int64_t rs2, int B, int N, float eps, int iters, float *dist,
+                                 int32_t *assignment, int32_t *stats, float grad_scale, float *grad_xyz1, float *sums,
+                                 void *workspace, size_t workspace_bytes, void *stream) {
     int rc = emd_check(xyz1, dtype1, xyz2, dtype2, B, N, "emd_fwd");
     if (rc) return rc;
     if (iters < 0) { set_error("emd_fwd: iters=%d", iters); return PCL_E_ARG; }
     if (B > 0 && (!dist || !assignment)) { set_error("emd_fwd: null output"); return PCL_E_ARG; }
-    if (B == 0) return PCL_OK;
     cudaStream_t st = (cudaStream_t)stream;
+    if (B == 0) {
+        if (sums) PCL_CUDA(cudaMemsetAsync(sums, 0, 3 * sizeof(float), st));
+        return PCL_OK;
+    }
+    if (sums && (!workspace || workspace_bytes < pcl_emd_workspace_bytes(B, N))) {
+        set_error("emd_fwd: the fused sum needs a workspace of %zu bytes (pcl_emd_workspace_bytes)", pcl_emd_workspace_bytes(B, N));
+        return PCL_E_WORKSPACE;
+    }
     DeviceInfo di;
     if ((rc = device_info(&di))) return rc;
     int flags = 0;
@@ -1082,11 +1145,16 @@ extern "C" int pcl_emd_fwd(const void *xyz1, int dtype1, int64_t bs1, int64_t rs
     at[0].val.clusterDim.x = cs; at[0].val.clusterDim.y = 1; at[0].val.clusterDim.z = 1;
     cfg.attrs = at; cfg.numAttrs = 1;
     const Pts p1{xyz1, bs1, rs1, dtype1}, p2{xyz2, bs2, rs2, dtype2};
+    unsigned char *rest = workspace ? (unsigned char *)workspace + emd_fused_bytes(B) : nullptr;  // behind the fused-epilogue header
+    const size_t rest_bytes = workspace_bytes > emd_fused_bytes(B) ? workspace_bytes - emd_fused_bytes(B) : 0;
+    unsigned *ticket = sums ? (unsigned *)workspace : nullptr;
+    double *part = sums ? (double *)((unsigned char *)workspace + 256) : nullptr;
+    if (sums) PCL_CUDA(cudaMemsetAsync(ticket, 0, sizeof(unsigned), st));
     // development aid: PCL_EMD_PROFILE=1 makes the workspace receive per-phase clock totals (B*cs*16 int64)
-    if (env.profile && !(flags & EMD_F_COLD) && workspace && workspace_bytes >= ((size_t)B * cs * 16 + 512) * sizeof(long long)) {
-        PCL_CUDA(cudaLaunchKernelEx(&cfg, emd_auction_kernel<true>, p1, p2, N, eps, iters, flags, pcap, wpb_max, items_target, dist, (int *)assignment, (int *)stats, (long long *)workspace, (unsigned char *)nullptr));
+    if (env.profile && !(flags & EMD_F_COLD) && rest && rest_bytes >= ((size_t)B * cs * 16 + 512) * sizeof(long long)) {
+        PCL_CUDA(cudaLaunchKernelEx(&cfg, emd_auction_kernel<true>, p1, p2, N, eps, iters, flags, pcap, wpb_max, items_target, dist, (int *)assignment, (int *)stats, (long long *)rest, (unsigned char *)nullptr, grad_scale, grad_xyz1, part, ticket, sums));
     } else {
-        PCL_CUDA(cudaLaunchKernelEx(&cfg, emd_auction_kernel<false>, p1, p2, N, eps, iters, flags, pcap, wpb_max, items_target, dist, (int *)assignment, (int *)stats, (long long *)nullptr, (unsigned char *)((flags & EMD_F_COLD) ? workspace : nullptr)));
+        PCL_CUDA(cudaLaunchKernelEx(&cfg, emd_auction_kernel<false>, p1, p2, N, eps, iters, flags, pcap, wpb_max, items_target, dist, (int *)assignment, (int *)stats, (long long *)nullptr, (unsigned char *)((flags & EMD_F_COLD) ? rest : nullptr), grad_scale, grad_xyz1, part, ticket, sums));
     }
     return PCL_OK;
 }
@@ -1128,7 +1196,7 @@ extern "C" int pcl_emd_weighted_reduce(const float *dist, const int32_t *matched
     if (!sums || (B > 0 && !dist) || (class_weights && !matched_label)) { set_error("emd_weighted_reduce: null argument"); return PCL_E_ARG; }
     if (!workspace || workspace_bytes < pcl_emd_workspace_bytes(B, N)) { set_error("emd_weighted_reduce: workspace too small"); return PCL_E_WORKSPACE; }
     cudaStream_t st = (cudaStream_t)stream;
-    double *part = (double *)workspace;
+    double *part = (double *)((unsigned char *)workspace + emd_fused_bytes(B));
     emd_wreduce_stage1<<<RED_BLOCKS, 256, 0, st>>>(dist, matched_label, class_weights, (size_t)B * N, C, part);
     PCL_CUDA(cudaGetLastError());
     emd_wreduce_stage2<<<1, 32, 0, st>>>(part, RED_BLOCKS, sums);

@@ -17,23 +17,43 @@ from torch.autograd import Function
 from . import _lib
 
 
-def emd_forward_raw(xyz1, xyz2, eps, iters, want_stats=False):
-    """One pcl_emd_fwd call.  Returns (dist, assignment, stats|None); stats int32 (B,8) =
-    [sum_t U_t, iterations run, extra GetMax qualifiers, cluster size, executed evals lo, hi, flags, tiles]."""
+_WS_BYTES = {}  # (B, N) -> pcl_emd_workspace_bytes: a pure function of the sizes (and the device's SM count), asked once
+
+
+def emd_workspace(b, n, dev):
+    """A workspace for one pcl_emd_* call (torch's caching allocator hands the same block back call after call)."""
+    wsb = _WS_BYTES.get((b, n))
+    if wsb is None:
+        wsb = _WS_BYTES[(b, n)] = _lib.lib().pcl_emd_workspace_bytes(b, n)
+    return torch.empty(wsb, device=dev, dtype=torch.uint8), wsb
+
+
+def emd_forward_raw(xyz1, xyz2, eps, iters, want_stats=False, want_epilogue=False):
+    """One pcl_emd_fwd(_fused) call.  Returns (dist, assignment, stats|None); stats int32 (B,8) =
+    [sum_t U_t, iterations run, extra GetMax qualifiers, cluster size, executed evals lo, hi, flags, tiles].
+    want_epilogue=True: returns (dist, assignment, stats, unit_grad, sums) with the fused loss epilogue of the same kernel --
+    unit_grad (B,N,3) = d(sum sqrt(dist)) / d xyz1 and sums (3,) = [sum sqrt(dist), B*N, mean] (include/pcl.h)."""
     _lib.require_cuda()
     L = _lib.lib()
     xyz1, xyz2 = _lib.as_points(xyz1), _lib.as_points(xyz2)
     b, n, c1 = xyz1.shape
     assert xyz2.shape[0] == b and xyz2.shape[1] == n and c1 >= 3 and xyz2.shape[2] >= 3
     dev = xyz1.device
-    with torch.cuda.device(dev):
+    with _lib.on_device(dev):
         dist = torch.empty(b, n, device=dev, dtype=torch.float32)
         assignment = torch.empty(b, n, device=dev, dtype=torch.int32)
         stats = torch.empty(b, 8, device=dev, dtype=torch.int32) if want_stats else None
-        wsb = L.pcl_emd_workspace_bytes(b, n)
-        ws = torch.empty(wsb, device=dev, dtype=torch.uint8)
+        ws, wsb = emd_workspace(b, n, dev)
+        if want_epilogue:
+            unit_grad = torch.empty(b, n, 3, device=dev, dtype=torch.float32)
+            sums = torch.empty(3, device=dev, dtype=torch.float32)
+            rc = L.pcl_emd_fwd_fused(*_lib.pts_args(xyz1), *_lib.pts_args(xyz2), b, n, float(eps), int(iters),
+                                     dist.data_ptr(), assignment.data_ptr(), _lib.ptr(stats), 1.0, unit_grad.data_ptr(), sums.data_ptr(),
+                                     ws.data_ptr(), wsb, _lib.stream_ptr(dev))
+            _lib.check(rc, "pcl_emd_fwd_fused")
+            return dist, assignment, stats, unit_grad, sums
         rc = L.pcl_emd_fwd(*_lib.pts_args(xyz1), *_lib.pts_args(xyz2), b, n, float(eps), int(iters),
-                           dist.data_ptr(), assignment.data_ptr(), _lib.ptr(stats), ws.data_ptr(), wsb, _lib.stream_ptr())
+                           dist.data_ptr(), assignment.data_ptr(), _lib.ptr(stats), ws.data_ptr(), wsb, _lib.stream_ptr(dev))
         _lib.check(rc, "pcl_emd_fwd")
     return dist, assignment, stats
 
@@ -58,10 +78,10 @@ class emdFunction(Function):
         L = _lib.lib()
         b, n, _ = xyz1.shape
         graddist = graddist.contiguous().float()
-        with torch.cuda.device(xyz1.device):
+        with _lib.on_device(xyz1.device):
             gradxyz1 = torch.empty(b, n, 3, device=xyz1.device, dtype=torch.float32)
             rc = L.pcl_emd_bwd(*_lib.pts_args(xyz1), *_lib.pts_args(xyz2), b, n, assignment.data_ptr(),
-                               graddist.data_ptr(), gradxyz1.data_ptr(), _lib.stream_ptr())
+                               graddist.data_ptr(), gradxyz1.data_ptr(), _lib.stream_ptr(xyz1.device))
             _lib.check(rc, "pcl_emd_bwd")
         if xyz1.shape[2] != 3:  # caller passed more channels than xyz: only xyz receives gradient
             full = torch.zeros(xyz1.shape, device=xyz1.device, dtype=torch.float32)

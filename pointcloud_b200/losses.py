@@ -12,7 +12,7 @@ from torch.autograd import Function
 
 from . import _lib, cfg
 from .chamfer import chamfer_distance
-from .emd_module import emdModule, emd_forward_raw
+from .emd_module import emdModule, emd_forward_raw, emd_workspace
 
 
 class FilterClasses:
@@ -58,12 +58,12 @@ class FilteringChamferDistance:
             import ctypes
             L = _lib.lib()
             b, n, _ = target.shape
-            with torch.cuda.device(target.device):
+            with _lib.on_device(target.device):
                 xyz = torch.empty(b, n, 3, device=target.device, dtype=torch.float32)
                 num_points = torch.empty(b, device=target.device, dtype=torch.int64)
                 labels = (ctypes.c_int64 * len(f.whitelist))(*[int(v) for v in f.whitelist])
                 rc = L.pcl_class_filter(*_lib.pts_args(target), b, n, int(f.label_dim), labels, len(f.whitelist),
-                                        xyz.data_ptr(), num_points.data_ptr(), _lib.stream_ptr())
+                                        xyz.data_ptr(), num_points.data_ptr(), _lib.stream_ptr(target.device))
                 _lib.check(rc, "pcl_class_filter")
             return xyz, num_points
         if isinstance(f, FilterClasses) and target.dim() == 3:
@@ -111,12 +111,11 @@ class _MatchedPointLoss(Function):
         b, n = dist.shape
         dev = dist.device
         c = 0 if class_weights is None else class_weights.numel()
-        with torch.cuda.device(dev):
+        with _lib.on_device(dev):
             sums = torch.empty(2, device=dev, dtype=torch.float32)
-            wsb = L.pcl_emd_workspace_bytes(b, n)
-            ws = torch.empty(wsb, device=dev, dtype=torch.uint8)
+            ws, wsb = emd_workspace(b, n, dev)
             rc = L.pcl_emd_weighted_reduce(dist.data_ptr(), _lib.ptr(matched), _lib.ptr(class_weights), b, n, c,
-                                           sums.data_ptr(), ws.data_ptr(), wsb, _lib.stream_ptr())
+                                           sums.data_ptr(), ws.data_ptr(), wsb, _lib.stream_ptr(dev))
             _lib.check(rc, "pcl_emd_weighted_reduce")
         ctx.save_for_backward(xyz1, xyz2, dist, assignment, matched, class_weights)
         ctx.in_meta = (xyz1.dtype,)
@@ -133,18 +132,40 @@ class _MatchedPointLoss(Function):
         dev = dist.device
         c = 0 if class_weights is None else class_weights.numel()
         g = grad_sums.contiguous().float()
-        with torch.cuda.device(dev):
+        with _lib.on_device(dev):
             unit = torch.ones(2, device=dev, dtype=torch.float32)
             grad = torch.empty(b, n, 3, device=dev, dtype=torch.float32)
             rc = L.pcl_emd_weighted_bwd(*_lib.pts_args(xyz1), *_lib.pts_args(xyz2), b, n, assignment.data_ptr(),
                                         dist.data_ptr(), _lib.ptr(matched), _lib.ptr(class_weights), c,
-                                        unit.data_ptr(), g.data_ptr(), grad.data_ptr(), _lib.stream_ptr())
+                                        unit.data_ptr(), g.data_ptr(), grad.data_ptr(), _lib.stream_ptr(dev))
             _lib.check(rc, "pcl_emd_weighted_bwd")
         if xyz1.shape[2] != 3:
             full = torch.zeros(xyz1.shape, device=dev, dtype=torch.float32)
             full[:, :, :3] = grad
             grad = full
         return grad.to(ctx.in_meta[0]), None, None, None, None, None
+
+
+class _FusedPointLoss(Function):
+    """Unweighted point term (utils.py:304 with weights == 1): the sums and d(sum sqrt(dist))/d xyz1 were written by the
+    auction kernel's epilogue (pcl_emd_fwd_fused), so forward launches nothing and backward is one scale."""
+
+    @staticmethod
+    def forward(ctx, xyz1, unit_grad, sums):
+        ctx.save_for_backward(unit_grad)
+        ctx.in_meta = (xyz1.dtype, xyz1.shape)
+        return sums[:2].clone()
+
+    @staticmethod
+    def backward(ctx, grad_sums):
+        (unit_grad,) = ctx.saved_tensors
+        dt, shape = ctx.in_meta
+        grad = unit_grad * grad_sums[0]
+        if shape[2] != 3:
+            full = torch.zeros(shape, device=grad.device, dtype=torch.float32)
+            full[:, :, :3] = grad
+            grad = full
+        return grad.to(dt), None, None
 
 
 def matched_label_hist(target_label, assignment, num_classes):
@@ -154,11 +175,11 @@ def matched_label_hist(target_label, assignment, num_classes):
     b, n = assignment.shape
     dev = assignment.device
     lab = _lib.as_points(target_label)
-    with torch.cuda.device(dev):
+    with _lib.on_device(dev):
         hist = torch.empty(num_classes, device=dev, dtype=torch.int64)
         matched = torch.empty(b, n, device=dev, dtype=torch.int32)
         rc = L.pcl_emd_match_hist(*_lib.pts_args(lab), assignment.data_ptr(), b, n, num_classes, hist.data_ptr(),
-                                  matched.data_ptr(), _lib.stream_ptr())
+                                  matched.data_ptr(), _lib.stream_ptr(dev))
         _lib.check(rc, "pcl_emd_match_hist")
     return hist, matched
 
@@ -172,13 +193,13 @@ class _SegCrossEntropySums(Function):
         L = _lib.lib()
         b, n, c = logits.shape
         dev = logits.device
-        with torch.cuda.device(dev):
+        with _lib.on_device(dev):
             sums = torch.empty(2, device=dev, dtype=torch.float32)
             pred_hist = torch.empty(c, device=dev, dtype=torch.int64)
             wsb = L.pcl_emd_feature_workspace_bytes()
             ws = torch.empty(wsb, device=dev, dtype=torch.uint8)
             rc = L.pcl_emd_seg_ce_fwd(*_lib.pts_args(logits), matched.data_ptr(), class_weights.data_ptr(), b, n, c,
-                                      sums.data_ptr(), pred_hist.data_ptr(), ws.data_ptr(), wsb, _lib.stream_ptr())
+                                      sums.data_ptr(), pred_hist.data_ptr(), ws.data_ptr(), wsb, _lib.stream_ptr(dev))
             _lib.check(rc, "pcl_emd_seg_ce_fwd")
         ctx.save_for_backward(logits, matched, class_weights)
         ctx.mark_non_differentiable(pred_hist)
@@ -191,10 +212,10 @@ class _SegCrossEntropySums(Function):
         b, n, c = logits.shape
         dev = logits.device
         g = grad_sums.contiguous().float()
-        with torch.cuda.device(dev):
+        with _lib.on_device(dev):
             grad = torch.empty(b, n, c, device=dev, dtype=torch.float32)
             rc = L.pcl_emd_seg_ce_bwd(*_lib.pts_args(logits), matched.data_ptr(), class_weights.data_ptr(), b, n, c,
-                                      g.data_ptr(), grad.data_ptr(), _lib.stream_ptr())
+                                      g.data_ptr(), grad.data_ptr(), _lib.stream_ptr(dev))
             _lib.check(rc, "pcl_emd_seg_ce_bwd")
         return grad.to(logits.dtype), None, None
 
@@ -208,12 +229,12 @@ class _MatchedFeatureMSESums(Function):
         L = _lib.lib()
         b, n, f = feat.shape
         dev = feat.device
-        with torch.cuda.device(dev):
+        with _lib.on_device(dev):
             sums = torch.empty(2, device=dev, dtype=torch.float32)
             wsb = L.pcl_emd_feature_workspace_bytes()
             ws = torch.empty(wsb, device=dev, dtype=torch.uint8)
             rc = L.pcl_emd_feat_mse_fwd(*_lib.pts_args(feat), *_lib.pts_args(tfeat), assignment.data_ptr(), b, n, f,
-                                        sums.data_ptr(), ws.data_ptr(), wsb, _lib.stream_ptr())
+                                        sums.data_ptr(), ws.data_ptr(), wsb, _lib.stream_ptr(dev))
             _lib.check(rc, "pcl_emd_feat_mse_fwd")
         ctx.save_for_backward(feat, tfeat, assignment)
         return sums
@@ -225,10 +246,10 @@ class _MatchedFeatureMSESums(Function):
         b, n, f = feat.shape
         dev = feat.device
         g = grad_sums.contiguous().float()
-        with torch.cuda.device(dev):
+        with _lib.on_device(dev):
             grad = torch.empty(b, n, f, device=dev, dtype=torch.float32)
             rc = L.pcl_emd_feat_mse_bwd(*_lib.pts_args(feat), *_lib.pts_args(tfeat), assignment.data_ptr(), b, n, f,
-                                        g.data_ptr(), grad.data_ptr(), _lib.stream_ptr())
+                                        g.data_ptr(), grad.data_ptr(), _lib.stream_ptr(dev))
             _lib.check(rc, "pcl_emd_feat_mse_bwd")
         return grad.to(feat.dtype), None, None
 
@@ -287,10 +308,12 @@ class EarthMoverDistance:
         return F.kl_div(F.log_softmax(pred_distribution.float(), dim=0), F.softmax(distribution, dim=0), reduction='batchmean')  # :283
 
     # -- the places where the fused path enters the CUDA library (overridden only by CPU host-logic tests)
-    def _auction(self, pred, target):
+    def _auction(self, pred, target, want_epilogue=False):
+        """(xyz1, xyz2, dists, assignment[, unit_grad, sums]): the last two come from the kernel's fused epilogue and are
+        only asked for by the unweighted loss; an override may ignore the flag and return four values."""
         xyz1, xyz2 = _lib.as_points(pred[:, :, :3]), _lib.as_points(target[:, :, :3])
-        dists, assignment, _ = emd_forward_raw(xyz1, xyz2, self.eps, self.iterations)
-        return xyz1, xyz2, dists, assignment
+        r = emd_forward_raw(xyz1, xyz2, self.eps, self.iterations, want_epilogue=want_epilogue)
+        return (xyz1, xyz2, r[0], r[1]) + tuple(r[3:])
 
     def _matched_hist(self, target, assignment):
         return matched_label_hist(target[:, :, 3:4], assignment, self.C)
@@ -310,7 +333,9 @@ class EarthMoverDistance:
         if not pred.is_cuda and type(self)._auction is EarthMoverDistance._auction:
             _lib.require_cuda()
             pred, target = pred.cuda(), target.cuda()
-        xyz1, xyz2, dists, assignment = self._auction(pred, target)
+        res = self._auction(pred, target, want_epilogue=(self.C is None))
+        xyz1, xyz2, dists, assignment = res[:4]
+        epilogue = res[4:] if len(res) == 6 else None   # (unit_grad, sums) of the fused kernel epilogue
 
         if cfg.debug:  # utils.py:261-265
             num_points = pred.shape[1]
@@ -331,7 +356,10 @@ class EarthMoverDistance:
             self.log('train_loss/cross_entropy', ce_l)
             self.log('train_loss/kl_divergence', kl_div)
         else:  # general feature loss (utils.py:300-301)
-            sums = self._point_sums(xyz1, xyz2, dists, assignment, None, None)
+            if epilogue is not None:
+                sums = _FusedPointLoss.apply(xyz1, epilogue[0], epilogue[1])
+            else:
+                sums = self._point_sums(xyz1, xyz2, dists, assignment, None, None)
             if pred.shape[2] == 3 or pred.numel() == 0:
                 matched_feat = target[:, :, 3:].take_along_dim(assignment.long().unsqueeze(-1), 1)
                 feature_l = F.mse_loss(pred[:, :, 3:], matched_feat)  # nan, exactly like the reference on empty features

@@ -19,9 +19,9 @@ def farthest_point_sample(xyz, npoint, start_idx=None, skip_origin=True):
     assert c >= 3
     dev = xyz.device
     st = None if start_idx is None else start_idx.to(device=dev, dtype=torch.int32).contiguous()
-    with torch.cuda.device(dev):
+    with _lib.on_device(dev):
         idx = torch.empty(b, int(npoint), device=dev, dtype=torch.int32)
-        rc = L.pcl_fps(*_lib.pts_args(xyz), b, n, int(npoint), _lib.ptr(st), 1 if skip_origin else 0, idx.data_ptr(), _lib.stream_ptr())
+        rc = L.pcl_fps(*_lib.pts_args(xyz), b, n, int(npoint), _lib.ptr(st), 1 if skip_origin else 0, idx.data_ptr(), _lib.stream_ptr(dev))
         _lib.check(rc, "pcl_fps")
     return idx.long()
 
@@ -50,8 +50,8 @@ def query_ball_point(radius, nsample, xyz, new_xyz):
     s = new_xyz.shape[1]
     dev = xyz.device
     r2 = float(torch.tensor(radius ** 2, dtype=torch.float32))  # the comparison happens in fp32 (sqrdists > radius ** 2)
-    with torch.cuda.device(dev):
+    with _lib.on_device(dev):
         out = torch.empty(b, s, int(nsample), device=dev, dtype=torch.int32)
-        rc = L.pcl_ball_query(*_lib.pts_args(xyz), *_lib.pts_args(new_xyz), b, n, s, r2, int(nsample), out.data_ptr(), _lib.stream_ptr())
+        rc = L.pcl_ball_query(*_lib.pts_args(xyz), *_lib.pts_args(new_xyz), b, n, s, r2, int(nsample), out.data_ptr(), _lib.stream_ptr(dev))
         _lib.check(rc, "pcl_ball_query")
     return out.long()

@@ -84,3 +84,46 @@ class ShardedLoss:
         g = _all_reduce_sum(torch.stack([ld * b_local, torch.full_like(ld, b_local)]), self.group)
         share = local * (b_local / g[1].float())                 # this rank's share of the global mean
         return (g[0] / g[1]).float() + scale * (share - share.detach())
+
+
+class ShardedChamferEmdStep:
+    """BASELINE config 2 on one rank's shard: Chamfer fwd+bwd and the unweighted EMD fwd + sqrt-mean + bwd of the local
+    clouds in ONE C-ABI call (`pcl_chamfer_emd_step`, three kernels, preallocated outputs) followed by the ONE collective
+    the sharded loss needs: an in-place all-reduce (NCCL over NVLink) of the four batch sums the call leaves contiguous,
+    [sum_n chamfer_x, sum_n chamfer_y, sum sqrt(dist), B_r*N].
+
+    After `step()` (asynchronous, on torch's current stream):
+      * `stats` (device view, fp32[4]) holds the all-reduced vector; `losses()` turns it into the GLOBAL loss scalars
+        {chamfer = ([0]+[1])/B_global, emd = [2]/[3]} -- what one GPU computes on the gathered batch;
+      * `grad_chamfer`, `grad_emd` (B_r,N,3) hold d(local mean)/d pred, i.e. world_size * d(global mean)/d(local pred) for
+        equal shards: exactly what DistributedDataParallel's gradient averaging expects (same contract as ShardedLoss).
+    """
+
+    def __init__(self, batch_local, points, device, eps=0.005, iters=50, chamfer_mode=0, process_group=None):
+        from . import _lib
+        self._lib, self.L = _lib, _lib.lib()
+        self.b, self.n, self.eps, self.iters, self.mode, self.group = int(batch_local), int(points), float(eps), int(iters), int(chamfer_mode), process_group
+        self.device = device
+        f32 = torch.float32
+        self.out = torch.zeros(8, device=device, dtype=f32)   # the `losses` vector of pcl_chamfer_emd_step (include/pcl.h)
+        self.stats = self.out[2:6]
+        self.grad_chamfer = torch.empty(self.b, self.n, 3, device=device, dtype=f32)
+        self.grad_emd = torch.empty(self.b, self.n, 3, device=device, dtype=f32)
+        self.scratch_bytes = self.L.pcl_chamfer_emd_step_scratch_bytes(self.b, self.n)
+        self.scratch = torch.empty(self.scratch_bytes, device=device, dtype=torch.uint8)
+        self.world = dist.get_world_size(process_group) if (dist.is_available() and dist.is_initialized()) else 1
+
+    def step(self, pred, target):
+        rc = self.L.pcl_chamfer_emd_step(*self._lib.pts_args(pred), *self._lib.pts_args(target), self.b, self.n, self.eps, self.iters, self.mode,
+                                         self.out.data_ptr(), self.grad_chamfer.data_ptr(), self.grad_emd.data_ptr(),
+                                         self.scratch.data_ptr(), self.scratch_bytes, self._lib.stream_ptr(self.device))
+        self._lib.check(rc, "pcl_chamfer_emd_step")
+        if self.world > 1:
+            dist.all_reduce(self.stats, op=dist.ReduceOp.SUM, group=self.group)
+        return self.stats
+
+    def losses(self):
+        """Global {chamfer, emd} as python floats (synchronises)."""
+        s = self.stats.double().cpu()
+        b_global = float(s[3]) / self.n
+        return {"chamfer": float(s[0] + s[1]) / b_global, "emd": float(s[2] / s[3])}

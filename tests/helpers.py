@@ -31,6 +31,29 @@ def ref_emd_backward(ref, xyz1, xyz2, graddist, assignment):
     return gradxyz1
 
 
+class RefEmdFunction(torch.autograd.Function):
+    """Restatement of the reference's emdFunction (emd_module.py:33-72) around the UNMODIFIED extension `ref` (oracle/_ref/emd.so):
+    forward = 12 zero-filled scratch tensors + emd.forward, backward = 2 zero fills + emd.backward; the target gets zeros.
+    Test / bench infrastructure: the reference's own emd_module.py is not available on the GPU box."""
+
+    @staticmethod
+    def forward(ctx, ref, xyz1, xyz2, eps, iters):
+        dist, assignment = ref_emd_forward(ref, xyz1, xyz2, eps, iters)
+        ctx.ref = ref
+        ctx.save_for_backward(xyz1.contiguous().float(), xyz2.contiguous().float(), assignment)
+        ctx.mark_non_differentiable(assignment)
+        return dist, assignment
+
+    @staticmethod
+    def backward(ctx, graddist, gradidx):
+        xyz1, xyz2, assignment = ctx.saved_tensors
+        graddist = graddist.contiguous()
+        gradxyz1 = torch.zeros(xyz1.size(), device='cuda').contiguous()
+        gradxyz2 = torch.zeros(xyz2.size(), device='cuda').contiguous()
+        ctx.ref.backward(xyz1, xyz2, gradxyz1, graddist, assignment)
+        return None, gradxyz1, gradxyz2, None, None
+
+
 def npy(t):
     return t.detach().cpu().numpy()
 

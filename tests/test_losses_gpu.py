@@ -133,7 +133,7 @@ def test_host_buffer_step_entry_point_matches_device_path():
     b, n = 4, 1024
     x1, x2 = synth.uniform_clouds(b, n, seed=12)
     ph, th = x1.pin_memory(), x2.pin_memory()
-    loss_h = torch.zeros(3).pin_memory()
+    loss_h = torch.zeros(8).pin_memory()      # {chamfer x, y means; chamfer x, y batch sums; sum sqrt(dist), B*N, EMD mean, -}
     gch, geh = torch.zeros(b, n, 3).pin_memory(), torch.zeros(b, n, 3).pin_memory()
     nbytes = L.pcl_loss_host_scratch_bytes(b, n)
     scratch = torch.empty(nbytes, dtype=torch.uint8, device="cuda")
@@ -151,7 +151,9 @@ def test_host_buffer_step_entry_point_matches_device_path():
     dist, _ = pcl.emdModule()(xe, x2.cuda(), 0.005, 50)
     el = dist.sqrt().mean()
     el.backward()
-    assert float(loss_h[2]) == pytest.approx(float(el), rel=1e-6)
+    assert float(loss_h[6]) == pytest.approx(float(el), rel=1e-6) and float(loss_h[5]) == b * n
+    assert float(loss_h[4]) == pytest.approx(float(dist.detach().sqrt().sum()), rel=1e-6)
+    assert float(loss_h[2] + loss_h[3]) == pytest.approx(b * float(cl), rel=1e-6)
     np.testing.assert_allclose(geh.numpy(), npy(xe.grad), rtol=REL, atol=1e-10)
     rc = L.pcl_chamfer_emd_step_host(ph.data_ptr(), th.data_ptr(), b, n, 0.005, 50, 0, loss_h.data_ptr(), None, None,
                                      scratch.data_ptr(), 16, st)
@@ -166,7 +168,7 @@ def test_composite_device_step_matches_separate_calls():
     pred, target = synth.autoencoder_batch(b, n, seed=21)
     pc, tc = pred.cuda(), target.cuda()
     px, tx = pc[:, :, :3], tc[:, :, :3]                         # strided views straight into the composite call
-    losses = torch.zeros(4, device="cuda")
+    losses = torch.zeros(8, device="cuda")
     gch, gem = torch.empty(b, n, 3, device="cuda"), torch.empty(b, n, 3, device="cuda")
     nbytes = L.pcl_chamfer_emd_step_scratch_bytes(b, n)
     scratch = torch.empty(nbytes, dtype=torch.uint8, device="cuda")
@@ -182,7 +184,7 @@ def test_composite_device_step_matches_separate_calls():
     dist, _ = pcl.emdModule()(xe, tx, 0.005, 50)
     el = dist.sqrt().mean()
     el.backward()
-    assert float(losses[0] + losses[1]) == pytest.approx(float(cl), rel=1e-6) and float(losses[2]) == pytest.approx(float(el), rel=1e-6)
+    assert float(losses[0] + losses[1]) == pytest.approx(float(cl), rel=1e-6) and float(losses[6]) == pytest.approx(float(el), rel=1e-6)
     np.testing.assert_allclose(npy(gch), npy(xg.grad), rtol=REL, atol=1e-9)
     np.testing.assert_allclose(npy(gem), npy(xe.grad), rtol=REL, atol=1e-10)
 
@@ -196,7 +198,7 @@ def test_composite_step_can_be_captured_in_a_cuda_graph():
     x1, x2 = synth.uniform_clouds(b, n, seed=40)
     y1, y2 = synth.uniform_clouds(b, n, seed=41)
     pin, tin = x1.cuda(), x2.cuda()
-    losses = torch.zeros(4, device="cuda")
+    losses = torch.zeros(8, device="cuda")
     gch, gem = torch.empty(b, n, 3, device="cuda"), torch.empty(b, n, 3, device="cuda")
     nbytes = L.pcl_chamfer_emd_step_scratch_bytes(b, n)
     scratch = torch.empty(nbytes, dtype=torch.uint8, device="cuda")
@@ -220,11 +222,11 @@ def test_composite_step_can_be_captured_in_a_cuda_graph():
     replay_b = losses.clone()
     call(torch.cuda.current_stream())
     torch.cuda.synchronize()
-    assert torch.equal(replay_b[:3], losses[:3]) and not torch.equal(direct_a[:3], replay_b[:3])
+    assert torch.equal(replay_b, losses) and not torch.equal(direct_a, replay_b)
     pin.copy_(x1.cuda()); tin.copy_(x2.cuda())
     graph.replay()
     torch.cuda.synchronize()
-    assert torch.equal(losses[:3], direct_a[:3])
+    assert torch.equal(losses, direct_a)
 
 
 def test_sharded_wrapper_single_rank_is_identity():

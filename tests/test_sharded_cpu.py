@@ -24,7 +24,7 @@ from pointcloud_b200.sharded import ShardedLoss, shard_bounds  # noqa: E402
 class CpuEMD(EarthMoverDistance):
     """EarthMoverDistance with its kernel entry points served by the CPU oracle / plain torch (tests only)."""
 
-    def _auction(self, pred, target):
+    def _auction(self, pred, target, want_epilogue=False):
         xyz1, xyz2 = pred[:, :, :3], target[:, :, :3]
         r = oracle.emd_forward(xyz1, xyz2, self.eps, self.iterations)
         return xyz1, xyz2, torch.from_numpy(r["dist"]), torch.from_numpy(r["assignment"])

@@ -25,6 +25,7 @@ for kind in ("uniform", "table", "noisy"):
         assert rc == 0
     torch.cuda.synchronize()
     cs = int(stats[0, 3])
+    ws = ws[256 + (max(b, 256) * 8 + 255) // 256 * 256:]  # behind the fused-epilogue header of the workspace (csrc/pcl_emd.cu emd_fused_bytes)
     prof = ws.view(torch.int64)[: b * cs * 16].view(b, cs, 16).double().cpu()
     tot = prof.sum(-1)
     print(f"{kind}: cs={cs} iters_run={stats[:,1].tolist()[:6]}.. per-CTA total cycles mean={tot.mean():.0f} max={tot.max():.0f}")
