@@ -2,8 +2,10 @@
 
   config 1: Chamfer fwd+bwd on the CPU, B=8, N=M=2048 (torch brute force = "reference torch path", and the oracle C port)
   config 3: weighted EMD (Segmenter loss) fwd+bwd, B=32, N=2048, C=5, through the Python loss class
-  config 5: Chamfer fwd+bwd, B=64, N=M in {1024..16384}, one GPU (C ABI, preallocated outputs)
-Writes one JSON object to stdout.  Run on the GPU box: python tools/bench_configs.py > gpurun_out/configs.json
+  config 5: Chamfer fwd+bwd, B=64 GLOBAL, N=M in {1024..16384}, on 1/2/4/8 GPUs (C ABI, preallocated outputs; B/G clouds per rank and
+            one all-reduce of the two batch sums per step inside the timed region)
+Writes one JSON object to stdout.  One GPU: python tools/bench_configs.py > gpurun_out/configs.json
+N GPUs (config 5 only): python -m torch.distributed.run --nproc-per-node N --master-addr 127.0.0.1 tools/bench_configs.py --only 5
 """
 import json
 import os
@@ -84,49 +86,64 @@ def config3():
     for regime in ("independent", "noisy"):
         pred, target = synth.segmenter_batch(b, n, seed=0, regime=regime)
         pg, tg = pred.cuda(), target.cuda()
-        for fused in (True, False):
-            fn = pcl.EarthMoverDistance(eps=0.005, its=50, num_classes=c, fused=fused)
+        fn = pcl.EarthMoverDistance(eps=0.005, its=50, num_classes=c)
 
-            def step():
-                p = pg.clone().requires_grad_()
-                loss = fn(p, tg)
-                loss.backward()
+        def step():
+            p = pg.detach().requires_grad_()
+            loss = fn(p, tg)
+            loss.backward()
 
-            ms = ev_time(step, 20)
-            out[f"{regime}_{'fused' if fused else 'reference_structure'}_ms"] = ms
-            out[f"{regime}_{'fused' if fused else 'reference_structure'}_clouds_per_s"] = b / (ms * 1e-3)
+        ms = ev_time(step, 20)
+        out[f"{regime}_ms"] = ms
+        out[f"{regime}_clouds_per_s"] = b / (ms * 1e-3)
     return out
 
 
 def config5():
+    import torch.distributed as dist
+    world, rank = int(os.environ.get("WORLD_SIZE", "1")), int(os.environ.get("RANK", "0"))
     L = _lib.lib()
     A = _lib.pts_args
-    b = 64
+    bg = 64
+    b = bg // world
     rows = []
     for n in (1024, 2048, 4096, 8192, 16384):
-        x, y = synth.uniform_clouds(b, n, seed=0)
-        x, y = x.cuda(), y.cuda()
+        xg, yg = synth.uniform_clouds(bg, n, seed=0)
+        x, y = xg[rank * b:(rank + 1) * b].cuda(), yg[rank * b:(rank + 1) * b].cuda()
         e = lambda *s, dt=torch.float32: torch.empty(*s, device="cuda", dtype=dt)
-        dx, dy, ix, iy, lxy = e(b, n), e(b, n), e(b, n, dt=torch.int32), e(b, n, dt=torch.int32), e(2)
+        dx, dy, ix, iy, lxy = e(b, n), e(b, n), e(b, n, dt=torch.int32), e(b, n, dt=torch.int32), e(4)
         gx, gy, ones = e(b, n, 3), e(b, n, 3), torch.ones(2, device="cuda")
         wsb = L.pcl_chamfer_workspace_bytes(b, n, n)
         ws = torch.empty(wsb, device="cuda", dtype=torch.uint8)
+        st = torch.cuda.current_stream().cuda_stream
 
         def fwd():
             assert L.pcl_chamfer_fwd(*A(x), None, *A(y), None, b, n, n, 3, 0, dx.data_ptr(), ix.data_ptr(), dy.data_ptr(), iy.data_ptr(),
-                                     lxy.data_ptr(), ws.data_ptr(), wsb, None) == 0
+                                     lxy.data_ptr(), ws.data_ptr(), wsb, st) == 0
 
         def bwd():
             assert L.pcl_chamfer_bwd(*A(x), None, *A(y), None, b, n, n, 3, ix.data_ptr(), iy.data_ptr(), ones.data_ptr(), gx.data_ptr(),
-                                     gy.data_ptr(), None) == 0
+                                     gy.data_ptr(), st) == 0
+
+        def step():  # the sharded Chamfer step: local kernels + the one collective on the two batch sums
+            fwd()
+            if world > 1:
+                dist.all_reduce(lxy[2:4])
+            bwd()
 
         it = 50 if n <= 4096 else 10
-        tf, tb = ev_time(fwd, it), ev_time(bwd, it)
+        if world > 1:
+            dist.barrier()
+        tf, tb, ts = ev_time(fwd, it), ev_time(bwd, it), ev_time(step, it)
+        if world > 1:
+            t = torch.tensor([tf, tb, ts], device="cuda", dtype=torch.float64)
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+            tf, tb, ts = (float(v) for v in t)
         evals = 2.0 * b * n * n
-        rows.append({"N": n, "fwd_ms": tf, "bwd_ms": tb, "clouds_per_s": b / ((tf + tb) * 1e-3),
-                     "directed_pair_evals_per_s": evals / (tf * 1e-3), "fp32_flop_frac_of_74.4T": 8 * evals / (tf * 1e-3) / 74.45e12,
+        rows.append({"N": n, "clouds_per_gpu": b, "fwd_ms": tf, "bwd_ms": tb, "step_ms": ts, "clouds_per_s": bg / (ts * 1e-3),
+                     "directed_pair_evals_per_s_per_gpu": evals / (tf * 1e-3), "fp32_flop_frac_of_74.4T": 8 * evals / (tf * 1e-3) / 74.45e12,
                      "bwd_GBps_algorithmic": 2 * b * n * 56 / (tb * 1e-3) / 1e9})
-    return {"B": b, "rows": rows}
+    return {"B_global": bg, "n_gpus": world, "scaling": "strong", "rows": rows}
 
 
 def demo_workload():
@@ -154,7 +171,25 @@ def demo_workload():
 
 
 if __name__ == "__main__":
-    res = {"gpu": torch.cuda.get_device_name(0), "config1_chamfer_cpu_B8_N2048": config1(), "config3_weighted_emd_B32_N2048_C5": config3(),
-           "config5_chamfer_sweep_B64": config5(), "reference_demo_B20_N8192": demo_workload(),
-           "config4": "not measured: needs the PointNet2 model zoo (SURVEY.md 2, out of scope) as the producer of pred"}
-    print(json.dumps(res, indent=1))
+    import argparse
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--only", default="")
+    args = ap.parse_args()
+    world, rank, local = int(os.environ.get("WORLD_SIZE", "1")), int(os.environ.get("RANK", "0")), int(os.environ.get("LOCAL_RANK", "0"))
+    torch.cuda.set_device(local)
+    if world > 1:
+        import torch.distributed as dist
+        sys.stdout.flush()
+        saved = os.dup(1); os.dup2(2, 1)  # NCCL's banner must not land in the JSON
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+        dist.barrier(); torch.cuda.synchronize()
+        sys.stdout.flush(); os.dup2(saved, 1); os.close(saved)
+    if args.only == "5" or world > 1:
+        res = {"gpu": torch.cuda.get_device_name(local), "config5_chamfer_sweep_B64": config5()}
+    else:
+        res = {"gpu": torch.cuda.get_device_name(0), "config1_chamfer_cpu_B8_N2048": config1(), "config3_weighted_emd_B32_N2048_C5": config3(),
+               "config5_chamfer_sweep_B64": config5(), "reference_demo_B20_N8192": demo_workload()}
+    if rank == 0:
+        print(json.dumps(res, indent=1))
+    if world > 1:
+        dist.destroy_process_group()
