@@ -105,7 +105,15 @@ PCL_API int pcl_chamfer_bwd(const void *x, int x_dtype, int64_t x_bs, int64_t x_
  * (>= pcl_emd_workspace_bytes(B, N), which then is tens of MB).
  * The GetMax race of the reference (emd_cuda.cu:188-191) is resolved deterministically: the
  * largest bidder index inside the +-1e-6 window wins.
+ *
+ * Two kernels implement the same auction bit for bit (stats[3] tells which one ran: cluster size, or 0 for the team kernel):
+ *   cluster path: one thread-block cluster of 1..16 CTAs per cloud for the whole auction (pcl_emd.cu);
+ *   team path:    one owner CTA per cloud + worker CTAs on all other SMs that execute Bid tasks of whichever cloud is
+ *                 furthest behind (pcl_emd_team.cu); needs N <= 3584, B < SM count and a workspace of pcl_emd_workspace_bytes.
+ * pcl_emd_set_path picks one for the calls that follow (process-wide); AUTO = the team path wherever it is possible.
  */
+enum { PCL_EMD_PATH_AUTO = 0, PCL_EMD_PATH_CLUSTER = 1, PCL_EMD_PATH_TEAM = 2 };
+PCL_API int pcl_emd_set_path(int path);
 PCL_API int pcl_emd_max_points(void);
 PCL_API size_t pcl_emd_workspace_bytes(int B, int N);
 PCL_API int pcl_emd_fwd(const void *xyz1, int dtype1, int64_t bs1, int64_t rs1,
