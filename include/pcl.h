@@ -112,7 +112,7 @@ PCL_API int pcl_chamfer_bwd(const void *x, int x_dtype, int64_t x_bs, int64_t x_
  *                 furthest behind (pcl_emd_team.cu); needs N <= 3584, B < SM count and a workspace of pcl_emd_workspace_bytes.
  * pcl_emd_set_path picks one for the calls that follow (process-wide); AUTO = the team path wherever it is possible.
  */
-enum { PCL_EMD_PATH_AUTO = 0, PCL_EMD_PATH_CLUSTER = 1, PCL_EMD_PATH_TEAM = 2 };
+enum { PCL_EMD_PATH_AUTO = 0, PCL_EMD_PATH_CLUSTER = 1, PCL_EMD_PATH_TEAM = 2, PCL_EMD_PATH_TICKETS = 3 };
 PCL_API int pcl_emd_set_path(int path);
 PCL_API int pcl_emd_max_points(void);
 PCL_API size_t pcl_emd_workspace_bytes(int B, int N);

@@ -36,20 +36,25 @@
 // "largest bidder index wins" (atomicMax), identical to oracle/emd_oracle.c.
 // Clouds of 3585..8192 points (EMD_SMEM_ONLY_N < N <= EMD_MAX_N) keep the hot half of the state (targets, prices) in
 // shared memory and the cold half (bids, per-object maxima, assignment arrays) in a per-CTA global-memory region.
-#include "pcl_emd_core.cuh"
+#include "pcl_emd_tasks.cuh"
 
 namespace pcl {
 namespace {
 
 // PROF: per-phase clock64() totals of thread 0 of every CTA -> prof[blockIdx.x*8 + phase] (development aid,
 // reached through the PCL_EMD_PROFILE environment variable; the product path instantiates PROF=false).
-template <bool PROF>
+// EXPORT: the lane-per-bidder iterations run as TICKETS (pcl_emd_tasks.cuh): the bidders' records go to the cloud's L2 region, the
+// CTAs of the cluster claim tasks dynamically (no static dealing, no waiting for the slowest CTA of the cluster), worker CTAs of a
+// second launch (emd_worker_kernel) claim them too -- they take work from the clouds that are furthest behind, which is what
+// shortens the launch: it ends with its slowest cloud -- and the bids come back as 16-byte records by list position (no scattered
+// distributed-shared-memory stores).  Iterations with few bidders keep the cluster-local warp-per-bidder path.
+template <bool PROF, bool EXPORT>
 __global__ void __launch_bounds__(EMD_THREADS, 1)
 emd_auction_kernel(Pts xyz1, Pts xyz2, int N, float eps, int iters, int flags, int pcap, int wpb_max, int items_target,
                    float *__restrict__ dist,
                    int *__restrict__ assignment, int *__restrict__ stats, long long *__restrict__ prof,
                    unsigned char *__restrict__ cold_ws, float grad_scale, float *__restrict__ grad_xyz1,
-                   double *__restrict__ part, unsigned *__restrict__ ticket, float *__restrict__ sums_out) {
+                   double *__restrict__ part, unsigned *__restrict__ ticket, float *__restrict__ sums_out, TeamWs W, int tasks_target, int export_pct, int lag_min_q, int lag_slope) {
     long long pt[16] = {0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0}, pc = 0, bid0 = 0;
 #define PCL_TICK(i)                                              \
     if constexpr (PROF) {                                        \
@@ -70,6 +75,21 @@ emd_auction_kernel(Pts xyz1, Pts xyz2, int N, float eps, int iters, int flags, i
 
     // ---- init: internal (Morton) order of both clouds, tiles, auction state (emd_module.py:45-56) ----------
     emd_setup(S, xyz1, xyz2, cloud, N, flags);
+    TeamCtl *const ctl = EXPORT ? &W.ctl[cloud] : nullptr;
+    unsigned char *const cl = EXPORT ? W.clouds + (size_t)cloud * W.stride : nullptr;
+    if constexpr (EXPORT) {
+        if (rank == 0 && W.nworkers > 0) {  // the mirror the workers load: targets (c = 3: price 0), prices, original target indices
+            __syncthreads();
+            copy16_out(cl + W.o_tgt, S.tgt, n32);
+            copy16_out(cl + W.o_pf, S.pf, n8 / 4);
+            if (S.tperm) copy16_out(cl + W.o_tperm, S.tperm, n8 / 8);
+        }
+    }
+    if constexpr (EXPORT) {
+        if (rank == 0 && tid == 0) atomicAdd(W.finished + 1, 1u);  // this cloud's CTAs are running (the workers' idle rule, pcl_emd_tasks.cuh)
+    }
+    unsigned tk_limit = 0;       // tickets published so far (identical in every CTA of the cluster)
+    bool told_workers = false;   // this cloud has no more exported iterations: said so once (rank 0)
     cluster.sync();  // every CTA's arrays exist before anyone writes remote bids
     PCL_TICK(0)
 
@@ -172,11 +192,23 @@ emd_auction_kernel(Pts xyz1, Pts xyz2, int N, float eps, int iters, int flags, i
         // (cluster size and dealing granularity are powers of two: shifts instead of integer divisions, which every thread
         // would otherwise execute in every iteration)
         const bool wpb = (U > 0 && ((U + cs - 1) >> csl) <= wpb_max);
+        // EXPORT: in a lane-per-bidder iteration the LAST blocks of the list (a share of export_pct percent) become tickets for the
+        // worker CTAs; the cluster deals the first Ud bidders among its CTAs as usual and serves the tickets the workers left over.
+        int Ud = U;
+        if constexpr (EXPORT) {
+            // How much is exported depends on how far this cloud lags behind the others (decided by rank 0 during the previous
+            // iteration, wsum[58..59] in every CTA): clouds that keep up export nothing and pay nothing, the slow ones -- the launch
+            // ends with the slowest -- hand up to export_pct percent of their bidders to the workers.
+            const int pct = (t > 0) ? S.wsum[58 + (t & 1)] : 0;  // two slots: rank 0 may write the next decision while a slow CTA still reads this one
+            if (!wpb && W.nworkers > 0 && pct > 0) Ud = (((U + 31) >> 5) - ((((U + 31) >> 5) * pct) / 100)) << 5;  // pct <= 60: Ud >= 32
+            Ud = min(Ud, U);
+        }
+        const bool ticketed = Ud < U;
         const int gsl = wpb ? 0 : 5, gsz = 1 << gsl;        // dealing granularity: 1 or 32 bidders
-        const int nblk = (U + gsz - 1) >> gsl;              // blocks in the list
+        const int nblk = (Ud + gsz - 1) >> gsl;             // blocks in the (statically dealt part of the) list
         const int myblk = (nblk > rank) ? ((nblk - rank + cs - 1) >> csl) : 0;  // blocks rank, rank+cs, ...
         int Uc = myblk << gsl;
-        if (myblk > 0 && (rank + (myblk - 1) * cs) == nblk - 1) Uc -= (nblk << gsl) - U;  // the last block may be short
+        if (myblk > 0 && (rank + (myblk - 1) * cs) == nblk - 1) Uc -= (nblk << gsl) - Ud;  // the last block may be short
         auto pos = [&](int b) -> int { return ((((b >> gsl) << csl) + rank) << gsl) + (b & (gsz - 1)); };
         const int Gn = (Uc + 31) >> 5;                                   // bidder groups (warps' worth)
         // tile slices per group: aim at ~2 work items per warp (dynamic queue), bounded by the partial buffer
@@ -203,6 +235,47 @@ emd_auction_kernel(Pts xyz1, Pts xyz2, int N, float eps, int iters, int flags, i
             }
         };
 
+        TaskHdr th = {};
+        unsigned tk_base = 0;
+        int prog_sum = 0;
+        if constexpr (EXPORT) {
+            if (rank == 0 && W.nworkers > 0) {  // progress of this cloud out, progress of all clouds in (consumed at the end of the bid phase)
+                if (tid == 0) *reinterpret_cast<volatile int *>(&ctl->prog) = wpb ? iters : t;
+                if (wid == EMD_WARPS - 1)
+                    for (int c = lane; c < (int)gridDim.x / cs; c += 32) prog_sum += (int)ld_relaxed_u32(reinterpret_cast<const unsigned *>(&W.ctl[c].prog));
+            }
+            if (rank == 0 && tid == 0 && !told_workers && wpb) atomicAdd(W.finished, 1u);  // U never grows: no exported iteration will follow
+            told_workers |= wpb;
+            if (ticketed) {
+                // The publisher of this iteration (the role rotates through the cluster) writes the exported bidders' records
+                // {x, y, z, seed threshold} and the boxes, then release-stores the ticket limit; no cluster barrier is needed.
+                const int Ux = U - Ud;
+                th = task_policy(Ux, false, tasks_target, NT, pcap);
+                tk_base = tk_limit;
+                tk_limit += (unsigned)((Ux + th.TB - 1) / th.TB);
+                if (rank == (t & (cs - 1))) {
+                    float4 *const g_brec = reinterpret_cast<float4 *>(cl + W.o_brec);
+                    unsigned short *const g_jp = reinterpret_cast<unsigned short *>(cl + W.o_jp);
+                    for (int i = tid; i < Ux; i += T) {
+                        const int jp = S.unass[Ud + i];
+                        const float3 a = pred_xyz(jp);
+                        unsigned lp = S.last[jp], lp34 = S.last34[jp];
+                        if (flags & EMD_F_SORT) first_seeds(jp, N, lp, lp34);
+                        g_brec[i] = make_float4(a.x, a.y, a.z, seed_threshold(S, lp, lp34, N, a.x, a.y, a.z));
+                        g_jp[i] = (unsigned short)jp;
+                    }
+                    copy16_out(cl + W.o_box, S.tlo, 2 * NT);  // boxes with this iteration's upper bounds of c
+                    __threadfence();
+                    __syncthreads();
+                    if (tid == 0) {
+                        ctl->t = t; ctl->U = th.U; ctl->TB = th.TB; ctl->KS = th.KS; ctl->mode = th.mode; ctl->base = (int)tk_base;
+                        __threadfence();
+                        st_release_u64(&ctl->avail, ((unsigned long long)(unsigned)(t + 1) << 32) | (unsigned long long)tk_limit);
+                    }
+                }
+                PCL_TICK(10)
+            }
+        }
         if (wpb) {
             // ---- few bidders: one WARP per bidder, one lane per target of a tile.  The tile tests are exact per
             // bidder (no other lane's neighbourhood keeps a tile alive), 32 boxes are tested per ballot, and the
@@ -440,11 +513,67 @@ emd_auction_kernel(Pts xyz1, Pts xyz2, int N, float eps, int iters, int flags, i
             }
         }
         PCL_TICK(7)
+        if constexpr (EXPORT) {
+            if (!wpb && rank == 0 && wid == EMD_WARPS - 1 && W.nworkers > 0) {  // export share of the NEXT iteration from the mean lag (in iterations)
+                const int nb = (int)gridDim.x / cs;
+                const float lag = (float)__reduce_add_sync(0xffffffffu, prog_sum) / (float)nb - (float)t;
+                int pct = 0;
+                if (lag >= 0.25f * (float)lag_min_q) pct = min(export_pct, 20 + (int)(lag * (float)lag_slope));
+                if (lane < cs) *cluster.map_shared_rank(S.wsum + 58 + ((t + 1) & 1), lane) = pct;  // read after the coming cluster barrier
+            }
+            if (ticketed) {
+                // tickets the workers have not taken: every CTA of the cluster serves them from its own replica
+                float4 *const g_brec = reinterpret_cast<float4 *>(cl + W.o_brec);
+                unsigned short *const g_jp = reinterpret_cast<unsigned short *>(cl + W.o_jp);
+                uint4 *const g_pub = reinterpret_cast<uint4 *>(cl + W.o_pub);
+                for (;;) {
+                    __syncthreads();  // the CTA is through with its own bids (partials, work counter) / with the previous ticket
+                    if (tid == 0) {
+                        int got = -1;
+                        for (;;) {
+                            const unsigned long long av = ld_acquire_u64(&ctl->avail);
+                            if ((unsigned)(av >> 32) != (unsigned)(t + 1)) { __nanosleep(32); continue; }  // the publisher is not there yet
+                            const unsigned nx = ld_relaxed_u32(&ctl->next);
+                            if (nx >= tk_limit) break;
+                            if (atomicCAS(&ctl->next, nx, nx + 1) == nx) { got = (int)(nx - tk_base); break; }
+                        }
+                        S.wsum[56] = got;
+                    }
+                    __syncthreads();
+                    const int task = S.wsum[56];
+                    if (task < 0) break;
+                    team_run_task(S, NT, eps, th, task, g_brec, g_jp, g_pub, my_evals);
+                    __threadfence();
+                    __syncthreads();
+                    if (tid == 0) { __threadfence(); atomicAdd(&ctl->done, 1u); }
+                }
+                PCL_TICK(11)
+                if (rank == 0 && tid == 0) {  // the tickets other CTAs hold (the barrier below makes the whole cluster wait with this thread)
+                    for (unsigned spin = 0; ld_acquire_u32(&ctl->done) < tk_limit; spin++) {
+                        if (spin > PCL_SPIN_LIMIT) __trap();
+                        __nanosleep(32);
+                    }
+                }
+            }
+        }
         cluster.sync();  // all bids of this iteration are visible in every CTA
         if constexpr (PROF) {
             if (blockIdx.x == 0 && tid == 0 && prof && t < 50) prof[(size_t)gridDim.x * 16 + t * 4 + 3] = clock64() - pc;
         }
         PCL_TICK(3)
+        if constexpr (EXPORT) {
+            if (ticketed) {  // all bids of the iteration are in the cloud's L2 region: bring them home, indexed by bidder
+                const uint4 *const g_pub = reinterpret_cast<const uint4 *>(cl + W.o_pub);
+                for (int q = tid; q < U - Ud; q += T) {
+                    const uint4 rec = __ldcg(&g_pub[q]);
+                    const int jp = S.unass[Ud + q];
+                    pub_cur[jp] = make_uint2(rec.x, rec.y);
+                    S.last34[jp] = rec.z;
+                }
+                __syncthreads();
+                PCL_TICK(9)
+            }
+        }
 
         // ---- 3. GetMax + Assign (emd_cuda.cu:181-215), replicated in every CTA -------------------------
         for (int q = tid; q < U; q += T) {
@@ -482,7 +611,14 @@ emd_auction_kernel(Pts xyz1, Pts xyz2, int N, float eps, int iters, int flags, i
             S.asg[jp] = (unsigned short)o;
             const float pnew = __fadd_rn(S.pf[o], __uint_as_float(pb.y));
             S.pf[o] = pnew;
-            S.tgt[o].w = __fsub_ru(3.0f, pnew);  // c = RU(3 - price): upper bound used by the filter
+            const float cnew = __fsub_ru(3.0f, pnew);  // c = RU(3 - price): upper bound used by the filter
+            S.tgt[o].w = cnew;
+            if constexpr (EXPORT) {
+                if (!wpb && W.nworkers > 0 && rank == ((t + 1) & (cs - 1))) {  // an exported iteration may follow (whether or not this one was): its publisher keeps the workers' mirror current (its own fence + release order these stores)
+                    reinterpret_cast<float *>(cl + W.o_pf)[o] = pnew;
+                    reinterpret_cast<float4 *>(cl + W.o_tgt)[o].w = cnew;
+                }
+            }
             S.maxinc[o] = -1e9f;
             S.maxidx[o] = -1;
         }
@@ -501,6 +637,9 @@ emd_auction_kernel(Pts xyz1, Pts xyz2, int N, float eps, int iters, int flags, i
         PCL_TICK(4)
     }
 
+    if constexpr (EXPORT) {
+        if (rank == 0 && tid == 0 && !told_workers) atomicAdd(W.finished, 1u);  // the auction ended inside its exported iterations
+    }
     // ---- CalcDist (emd_cuda.cu:217-226) + outputs in ORIGINAL index order; points split over the cluster ----
     // Fused loss epilogue of the unweighted EMD (utils.py:304 with weights == 1; emd_module.py:63-72 + emd_cuda.cu:284-300):
     //   grad_xyz1 = grad_scale * d(sum sqrt(dist)) / d xyz1 = 2 * (grad_scale / (2 sqrt(dist))) * (xyz1 - xyz2[assignment])
@@ -578,7 +717,8 @@ emd_auction_kernel(Pts xyz1, Pts xyz2, int N, float eps, int iters, int flags, i
             for (int w = 0; w < EMD_WARPS; w++) e += S.wsum[w];
             int *st = stats + (size_t)cloud * 8;
             st[0] = (int)sum_u; st[1] = iters_run; st[2] = e; st[3] = cs;
-            const unsigned long long ce = *S.evals;
+            unsigned long long ce = *S.evals;
+            if constexpr (EXPORT) ce += atomicAdd(&ctl->evals, 0ull);  // evaluations the workers executed for this cloud
             st[4] = (int)(ce & 0xffffffffull); st[5] = (int)(ce >> 32);
             st[6] = flags; st[7] = NT;
         }
@@ -694,7 +834,9 @@ int sm_count_or_default() {
     return di.sm_count;
 }
 
-int pick_cluster(int B, int N, int sm_count, size_t smem, cudaStream_t st) {
+struct EmdEnv;
+const EmdEnv &emd_env();
+int pick_cluster_impl(int B, int N, int sm_count, size_t smem, cudaStream_t st, int forced_cs) {
     // the occupancy query costs a few microseconds of host time: remembered per (device, B, shared-memory size)
     struct Memo { int dev, B; size_t smem; int cs; };
     static thread_local Memo memo[8];
@@ -704,7 +846,11 @@ int pick_cluster(int B, int N, int sm_count, size_t smem, cudaStream_t st) {
     for (int i = 0; i < memo_n; i++)
         if (memo[i].dev == dev && memo[i].B == B && memo[i].smem == smem) return memo[i].cs;
     int cs = cluster_size_for(B, sm_count);
-    while (cs > 1) {  // is a cluster of this size schedulable with this much shared memory?
+    if (forced_cs > 0) cs = forced_cs;  // development aid (PCL_EMD_CS)
+    // Are B clusters of this size resident at the same time with this much shared memory?  A cluster lives inside one GPC, so
+    // fewer clusters than B * cs <= SM count suggests may fit (8 clusters of 16 never do on a B200); a second wave would
+    // double the time of the launch, half the cluster size costs far less.
+    while (cs > 1) {
         cudaLaunchConfig_t cfg = {};
         cfg.gridDim = dim3(B * cs); cfg.blockDim = dim3(EMD_THREADS); cfg.dynamicSmemBytes = smem; cfg.stream = st;
         cudaLaunchAttribute at[1];
@@ -712,8 +858,8 @@ int pick_cluster(int B, int N, int sm_count, size_t smem, cudaStream_t st) {
         at[0].val.clusterDim.x = cs; at[0].val.clusterDim.y = 1; at[0].val.clusterDim.z = 1;
         cfg.attrs = at; cfg.numAttrs = 1;
         int ncl = 0;
-        cudaError_t e = cudaOccupancyMaxActiveClusters(&ncl, emd_auction_kernel<false>, &cfg);
-        if (e == cudaSuccess && ncl > 0) break;
+        cudaError_t e = cudaOccupancyMaxActiveClusters(&ncl, emd_auction_kernel<false, false>, &cfg);
+        if (e == cudaSuccess && ncl >= B) break;
         (void)cudaGetLastError();
         cs >>= 1;
     }
@@ -723,7 +869,7 @@ int pick_cluster(int B, int N, int sm_count, size_t smem, cudaStream_t st) {
 }
 
 // development aids, read once per process: PCL_EMD_NO_SORT, PCL_EMD_PCAP, PCL_EMD_WPB, PCL_EMD_ITEMS, PCL_EMD_PROFILE, PCL_EMD_TEAM*
-struct EmdEnv { bool no_sort, profile; int pcap, wpb, items, team, team_tasks, team_local, team_wpb, team_grid; };
+struct EmdEnv { bool no_sort, profile; int pcap, wpb, items, cs, path, team_tasks, team_local, team_wpb, team_grid, team_idle, team_export, team_lagmin, team_slope; };
 const EmdEnv &emd_env() {
     static const EmdEnv e = [] {
         EmdEnv v;
@@ -733,15 +879,22 @@ const EmdEnv &emd_env() {
         v.pcap = (s = getenv("PCL_EMD_PCAP")) ? atoi(s) * 32 : 0;
         v.wpb = (s = getenv("PCL_EMD_WPB")) ? atoi(s) : -1;
         v.items = (s = getenv("PCL_EMD_ITEMS")) ? atoi(s) : 0;
-        v.team = (s = getenv("PCL_EMD_TEAM")) ? atoi(s) : -1;              // 0: cluster kernel, 1: team kernel, unset: automatic
+        v.cs = (s = getenv("PCL_EMD_CS")) ? atoi(s) : 0;
+        v.path = (s = getenv("PCL_EMD_PATH")) ? atoi(s) : 0;               // PCL_EMD_PATH_* of include/pcl.h when pcl_emd_set_path says AUTO
+        v.team_export = (s = getenv("PCL_EMD_TEAM_EXPORT")) ? atoi(s) : -1;  // percent of a lane-per-bidder iteration's bidders exported as tickets
+        v.team_lagmin = (s = getenv("PCL_EMD_TEAM_LAGMIN")) ? atoi(s) : -1;  // quarter iterations behind the mean from which a cloud exports
+        v.team_slope = (s = getenv("PCL_EMD_TEAM_SLOPE")) ? atoi(s) : -1;    // exported percent per iteration of lag
+        v.team_idle = (s = getenv("PCL_EMD_TEAM_IDLE")) ? atoi(s) : 0;     // cycles without a ticket after which a worker of the ticket path leaves
         v.team_tasks = (s = getenv("PCL_EMD_TEAM_TASKS")) ? atoi(s) : 0;   // tasks per cloud and iteration the owner aims at
         v.team_local = (s = getenv("PCL_EMD_TEAM_LOCAL")) ? atoi(s) : -1;  // the owner works alone with at most this many bidders
         v.team_wpb = (s = getenv("PCL_EMD_TEAM_WPB")) ? atoi(s) : -1;      // warp-per-bidder tasks with at most this many bidders
-        v.team_grid = (s = getenv("PCL_EMD_TEAM_GRID")) ? atoi(s) : 0;     // CTAs of the team launch (default: one per SM)
+        v.team_grid = (s = getenv("PCL_EMD_TEAM_GRID")) ? atoi(s) : 0;     // CTAs of the team launch / clusters + workers of the ticket path (default: one per SM; -1: no workers)
         return v;
     }();
     return e;
 }
+
+int pick_cluster(int B, int N, int sm_count, size_t smem, cudaStream_t st) { return pick_cluster_impl(B, N, sm_count, smem, st, emd_env().cs); }
 
 }  // namespace
 
@@ -751,7 +904,31 @@ int emd_team_launch(const Pts &p1, const Pts &p2, int B, int N, float eps, int i
                     int local_max, int grid, size_t smem, float *dist, int *assignment, int *stats, void *team_ws, float grad_scale,
                     float *grad_xyz1, double *part, unsigned *ticket, float *sums, long long *prof, cudaStream_t st);
 
+int emd_worker_launch(void *team_ws, int B, int N, float eps, int flags, int pcap, int nworkers, size_t smem, long long idle_limit,
+                      long long *prof, cudaStream_t st);
+
 static int g_emd_path = PCL_EMD_PATH_AUTO;  // pcl_emd_set_path
+
+// library-owned stream for the worker launch of the ticket path (forked from / joined to the caller's stream with events)
+struct WorkerStream {
+    int dev = -1;
+    cudaStream_t side = nullptr;
+    cudaEvent_t fork = nullptr, join = nullptr;
+};
+static int worker_stream(WorkerStream **out) {
+    static thread_local WorkerStream ws;
+    int dev = 0;
+    PCL_CUDA(cudaGetDevice(&dev));
+    if (ws.dev != dev) {
+        if (ws.side) { cudaStreamDestroy(ws.side); cudaEventDestroy(ws.fork); cudaEventDestroy(ws.join); ws = WorkerStream(); }
+        PCL_CUDA(cudaStreamCreateWithFlags(&ws.side, cudaStreamNonBlocking));
+        PCL_CUDA(cudaEventCreateWithFlags(&ws.fork, cudaEventDisableTiming));
+        PCL_CUDA(cudaEventCreateWithFlags(&ws.join, cudaEventDisableTiming));
+        ws.dev = dev;
+    }
+    *out = &ws;
+    return PCL_OK;
+}
 }  // namespace pcl
 
 using namespace pcl;
@@ -759,7 +936,7 @@ using namespace pcl;
 extern "C" int pcl_emd_max_points(void) { return EMD_MAX_N; }
 
 extern "C" int pcl_emd_set_path(int path) {
-    if (path != PCL_EMD_PATH_AUTO && path != PCL_EMD_PATH_CLUSTER && path != PCL_EMD_PATH_TEAM) { set_error("emd_set_path: %d", path); return PCL_E_ARG; }
+    if (path < PCL_EMD_PATH_AUTO || path > PCL_EMD_PATH_TICKETS) { set_error("emd_set_path: %d", path); return PCL_E_ARG; }
     g_emd_path = path;
     return PCL_OK;
 }
@@ -841,36 +1018,52 @@ extern "C" int pcl_emd_fwd_fused(const void *xyz1, int dtype1, int64_t bs1, int6
     int dev = 0;
     PCL_CUDA(cudaGetDevice(&dev));
     if (attr_dev != dev) {
-        PCL_CUDA(cudaFuncSetAttribute(emd_auction_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, di.max_smem_optin));
-        PCL_CUDA(cudaFuncSetAttribute(emd_auction_kernel<false>, cudaFuncAttributeNonPortableClusterSizeAllowed, 1));
-        PCL_CUDA(cudaFuncSetAttribute(emd_auction_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, di.max_smem_optin));
-        PCL_CUDA(cudaFuncSetAttribute(emd_auction_kernel<true>, cudaFuncAttributeNonPortableClusterSizeAllowed, 1));
+        const void *kernels[4] = {(const void *)emd_auction_kernel<false, false>, (const void *)emd_auction_kernel<true, false>,
+                                  (const void *)emd_auction_kernel<false, true>, (const void *)emd_auction_kernel<true, true>};
+        for (const void *k : kernels) {
+            PCL_CUDA(cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, di.max_smem_optin));
+            PCL_CUDA(cudaFuncSetAttribute(k, cudaFuncAttributeNonPortableClusterSizeAllowed, 1));
+        }
         attr_dev = dev;
     }
     unsigned *ticket = sums ? (unsigned *)workspace : nullptr;
     double *part = sums ? (double *)((unsigned char *)workspace + 256) : nullptr;
     if (sums) PCL_CUDA(cudaMemsetAsync(ticket, 0, sizeof(unsigned), st));
     const Pts p1{xyz1, bs1, rs1, dtype1}, p2{xyz2, bs2, rs2, dtype2};
-    // Owner + worker kernel (pcl_emd_team.cu) whenever the batch leaves SMs for workers and the caller gave a workspace; the
-    // cluster kernel below otherwise (large clouds, B >= SM count, no workspace) or on request (pcl_emd_set_path / PCL_EMD_TEAM).
-    {
-        int path = g_emd_path;
-        if (path == PCL_EMD_PATH_AUTO && env.team >= 0) path = env.team ? PCL_EMD_PATH_TEAM : PCL_EMD_PATH_CLUSTER;
-        const size_t team_bytes = emd_team_workspace_bytes(B, N), all_bytes = pcl_emd_workspace_bytes(B, N);
-        const bool can = !(flags & EMD_F_COLD) && B < di.sm_count && team_bytes > 0 && workspace && workspace_bytes >= all_bytes;
-        if (path == PCL_EMD_PATH_TEAM && !can) { set_error("emd_fwd: the team path needs N <= %d, B < %d and a workspace of pcl_emd_workspace_bytes", EMD_SMEM_ONLY_N, di.sm_count); return PCL_E_UNSUPPORTED; }
-        if (can && path != PCL_EMD_PATH_CLUSTER) {
-            int grid = env.team_grid > 0 ? env.team_grid : di.sm_count;
-            if (grid < B) grid = B;
-            const int tasks_target = env.team_tasks > 0 ? env.team_tasks : (3 * grid / B + 1) / 2;  // ~1.5 tasks per CTA that can work on a cloud
-            const int local_max = env.team_local >= 0 ? env.team_local : 32;
-            const int team_wpb = env.team_wpb >= 0 ? env.team_wpb : 4 * EMD_WPB_MAX;
-            return emd_team_launch(p1, p2, B, N, eps, iters, flags, pcap, team_wpb, tasks_target, local_max, grid, smem, dist, (int *)assignment,
-                                   (int *)stats, (unsigned char *)workspace + (all_bytes - team_bytes), grad_scale, grad_xyz1, part, ticket, sums,
-                                   env.profile ? (long long *)((unsigned char *)workspace + emd_fused_bytes(B)) : nullptr, st);  // profile counters: 16 int64 per CTA (<= 256 CTAs fit the profile region)
-        }
+    // Which kernel (include/pcl.h, pcl_emd_set_path; development aid PCL_EMD_PATH):
+    //   tickets: cluster kernel whose lane-per-bidder iterations run as tickets + worker CTAs on the SMs the clusters leave free;
+    //   team:    one owner CTA per cloud + workers (pcl_emd_team.cu);
+    //   cluster: the plain cluster kernel (the only one for large clouds, B >= SM count or without a workspace).
+    int path = g_emd_path;
+    if (path == PCL_EMD_PATH_AUTO && env.path > 0) path = env.path;
+    const size_t team_bytes = emd_team_workspace_bytes(B, N), all_bytes = pcl_emd_workspace_bytes(B, N);
+    const bool can = !(flags & EMD_F_COLD) && B < di.sm_count && team_bytes > 0 && workspace && workspace_bytes >= all_bytes;
+    if ((path == PCL_EMD_PATH_TEAM || path == PCL_EMD_PATH_TICKETS) && !can) {
+        set_error("emd_fwd: the team / ticket paths need N <= %d, B < %d and a workspace of pcl_emd_workspace_bytes", EMD_SMEM_ONLY_N, di.sm_count);
+        return PCL_E_UNSUPPORTED;
     }
     const int cs = pick_cluster(B, N, di.sm_count, smem, st);
+    if (path == PCL_EMD_PATH_AUTO) {
+        // Measured on B200 over B = 1..128, N = 1024 / 2048 / 3584, early- and late-training inputs (profiles/r2_s2_path_sweep*.txt), judged
+        // on the sum of both regimes: big clouds are throughput-bound -> owner + workers; small clusters (many clouds) or many free SMs
+        // -> clusters + workers on the free SMs; otherwise (B <= 12, and the B = 32 launch of the benchmark, which leaves only 20 SMs)
+        // the plain cluster kernel, whose distributed-shared-memory exchange has the lowest latency per iteration.
+        const int free_sms = di.sm_count - B * cs;
+        path = PCL_EMD_PATH_CLUSTER;
+        if (can && N >= 3072 && B >= 8) path = PCL_EMD_PATH_TEAM;
+        else if (can && N >= 1536 && B >= 8 && (cs <= 2 || (cs == 4 && free_sms >= 48))) path = PCL_EMD_PATH_TICKETS;
+    }
+    void *team_ws = can ? (unsigned char *)workspace + (all_bytes - team_bytes) : nullptr;
+    long long *prof_team = env.profile && workspace ? (long long *)((unsigned char *)workspace + emd_fused_bytes(B)) : nullptr;  // 16 int64 per CTA, <= 256 CTAs
+    if (path == PCL_EMD_PATH_TEAM) {
+        int grid = env.team_grid > 0 ? env.team_grid : di.sm_count;
+        if (grid < B) grid = B;
+        const int tasks_target = env.team_tasks > 0 ? env.team_tasks : (3 * grid / B + 1) / 2;  // ~1.5 tasks per CTA that can work on a cloud
+        const int local_max = env.team_local >= 0 ? env.team_local : 32;
+        const int team_wpb = env.team_wpb >= 0 ? env.team_wpb : 4 * EMD_WPB_MAX;
+        return emd_team_launch(p1, p2, B, N, eps, iters, flags, pcap, team_wpb, tasks_target, local_max, grid, smem, dist, (int *)assignment,
+                               (int *)stats, team_ws, grad_scale, grad_xyz1, part, ticket, sums, prof_team, st);
+    }
     cudaLaunchConfig_t cfg = {};
     cfg.gridDim = dim3(B * cs); cfg.blockDim = dim3(EMD_THREADS); cfg.dynamicSmemBytes = smem; cfg.stream = st;
     cudaLaunchAttribute at[1];
@@ -879,11 +1072,46 @@ extern "C" int pcl_emd_fwd_fused(const void *xyz1, int dtype1, int64_t bs1, int6
     cfg.attrs = at; cfg.numAttrs = 1;
     unsigned char *rest = workspace ? (unsigned char *)workspace + emd_fused_bytes(B) : nullptr;  // behind the fused-epilogue header
     const size_t rest_bytes = workspace_bytes > emd_fused_bytes(B) ? workspace_bytes - emd_fused_bytes(B) : 0;
+    const bool prof_ok = env.profile && !(flags & EMD_F_COLD) && rest && rest_bytes >= ((size_t)B * cs * 16 + 512) * sizeof(long long);
+    if (path == PCL_EMD_PATH_TICKETS) {
+        int nworkers = env.team_grid > 0 ? env.team_grid - B * cs : di.sm_count - B * cs;  // the SMs the clusters leave free
+        if (nworkers < 0 || env.team_grid == -1) nworkers = 0;
+        const int tasks_target = env.team_tasks > 0 ? env.team_tasks : max(4, (2 * nworkers + B - 1) / B);  // exported tickets per cloud and iteration: ~2 per worker that serves the cloud, at least 4 (swept 2..8 at B=32)
+                int export_pct = env.team_export >= 0 ? env.team_export : 50;  // upper limit of the exported share (percent)
+        if (export_pct > 60) export_pct = 60;
+        const int lag_min_q = env.team_lagmin >= 0 ? env.team_lagmin : 4;   // a cloud exports when it lags >= this many quarter iterations behind the mean
+        const int lag_slope = env.team_slope >= 0 ? env.team_slope : 5;     // exported percent = 20 + slope * lag
+        const TeamWs W = team_ws_make(team_ws, B, N, nworkers);
+        PCL_CUDA(cudaMemsetAsync(team_ws, 0, team_ctl_bytes(B), st));
+        WorkerStream *ws = nullptr;
+        if (nworkers > 0) {
+            int rc2 = worker_stream(&ws);
+            if (rc2) return rc2;
+            PCL_CUDA(cudaEventRecord(ws->fork, st));  // the workers need the zeroed control block, nothing else
+        }
+        if (prof_ok) {
+            PCL_CUDA(cudaLaunchKernelEx(&cfg, emd_auction_kernel<true, true>, p1, p2, N, eps, iters, flags, pcap, wpb_max, items_target, dist, (int *)assignment, (int *)stats, (long long *)rest, (unsigned char *)nullptr, grad_scale, grad_xyz1, part, ticket, sums, W, tasks_target, export_pct, lag_min_q, lag_slope));
+        } else {
+            PCL_CUDA(cudaLaunchKernelEx(&cfg, emd_auction_kernel<false, true>, p1, p2, N, eps, iters, flags, pcap, wpb_max, items_target, dist, (int *)assignment, (int *)stats, (long long *)nullptr, (unsigned char *)nullptr, grad_scale, grad_xyz1, part, ticket, sums, W, tasks_target, export_pct, lag_min_q, lag_slope));
+        }
+        if (nworkers > 0) {
+            // Launched AFTER the clusters (they must not find their SMs taken) on a stream of their own; a worker leaves when every
+            // cloud is past its exported iterations, or after ~100 us without a ticket (so it can never starve a cluster of its SM).
+            PCL_CUDA(cudaStreamWaitEvent(ws->side, ws->fork, 0));
+            int rc2 = emd_worker_launch(team_ws, B, N, eps, flags, pcap, nworkers, smem, env.team_idle > 0 ? (long long)env.team_idle : 200000LL,
+                                        prof_ok ? (long long *)rest + (size_t)B * cs * 16 + 512 : nullptr, ws->side);
+            if (rc2) return rc2;
+            PCL_CUDA(cudaEventRecord(ws->join, ws->side));
+            PCL_CUDA(cudaStreamWaitEvent(st, ws->join, 0));  // the caller's next operation on `stream` comes after the workers
+        }
+        return PCL_OK;
+    }
+    const TeamWs W0 = {};
     // development aid: PCL_EMD_PROFILE=1 makes the workspace receive per-phase clock totals (B*cs*16 int64)
-    if (env.profile && !(flags & EMD_F_COLD) && rest && rest_bytes >= ((size_t)B * cs * 16 + 512) * sizeof(long long)) {
-        PCL_CUDA(cudaLaunchKernelEx(&cfg, emd_auction_kernel<true>, p1, p2, N, eps, iters, flags, pcap, wpb_max, items_target, dist, (int *)assignment, (int *)stats, (long long *)rest, (unsigned char *)nullptr, grad_scale, grad_xyz1, part, ticket, sums));
+    if (prof_ok) {
+        PCL_CUDA(cudaLaunchKernelEx(&cfg, emd_auction_kernel<true, false>, p1, p2, N, eps, iters, flags, pcap, wpb_max, items_target, dist, (int *)assignment, (int *)stats, (long long *)rest, (unsigned char *)nullptr, grad_scale, grad_xyz1, part, ticket, sums, W0, 0, 0, 0, 0));
     } else {
-        PCL_CUDA(cudaLaunchKernelEx(&cfg, emd_auction_kernel<false>, p1, p2, N, eps, iters, flags, pcap, wpb_max, items_target, dist, (int *)assignment, (int *)stats, (long long *)nullptr, (unsigned char *)((flags & EMD_F_COLD) ? rest : nullptr), grad_scale, grad_xyz1, part, ticket, sums));
+        PCL_CUDA(cudaLaunchKernelEx(&cfg, emd_auction_kernel<false, false>, p1, p2, N, eps, iters, flags, pcap, wpb_max, items_target, dist, (int *)assignment, (int *)stats, (long long *)nullptr, (unsigned char *)((flags & EMD_F_COLD) ? rest : nullptr), grad_scale, grad_xyz1, part, ticket, sums, W0, 0, 0, 0, 0));
     }
     return PCL_OK;
 }

@@ -15,6 +15,7 @@
 #endif
 
 namespace cg = cooperative_groups;
+
 constexpr int kScanUnroll = PCL_SCAN_UNROLL;  // groups of 4 targets per loop trip in the tile scan
 
 namespace pcl {

@@ -28,6 +28,16 @@ def emd_workspace(b, n, dev):
     return torch.empty(wsb, device=dev, dtype=torch.uint8), wsb
 
 
+EMD_PATHS = {"auto": 0, "cluster": 1, "team": 2, "tickets": 3}  # include/pcl.h PCL_EMD_PATH_*
+
+
+def set_emd_path(path="auto"):
+    """Which auction kernel the calls that follow use (process-wide; include/pcl.h pcl_emd_set_path): "auto", "cluster" (one
+    thread-block cluster per cloud), "team" (owner CTA per cloud + workers) or "tickets" (cluster kernel whose heavy iterations
+    are shared with worker CTAs).  All of them return bit-identical results; the choice is a tuning knob."""
+    _lib.check(_lib.lib().pcl_emd_set_path(EMD_PATHS[path] if isinstance(path, str) else int(path)), "pcl_emd_set_path")
+
+
 def emd_forward_raw(xyz1, xyz2, eps, iters, want_stats=False, want_epilogue=False):
     """One pcl_emd_fwd(_fused) call.  Returns (dist, assignment, stats|None); stats int32 (B,8) =
     [sum_t U_t, iterations run, extra GetMax qualifiers, cluster size, executed evals lo, hi, flags, tiles].

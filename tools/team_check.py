@@ -7,6 +7,7 @@ from pointcloud_b200 import _lib, synth
 
 L = _lib.lib()
 tag = sys.argv[1] if len(sys.argv) > 1 else ""
+alt = int(os.environ.get("ALT_PATH", "3"))  # PCL_EMD_PATH_* compared with the plain cluster kernel
 cases = [("table", 32, 2048), ("noisy", 32, 2048), ("uniform", 32, 2048), ("table", 4, 2048), ("noisy", 4, 2048), ("table", 1, 2048),
          ("table", 8, 2048), ("table", 16, 2048), ("table", 64, 2048), ("noisy", 64, 2048), ("table", 100, 2048), ("uniform", 5, 1000),
          ("uniform", 2, 333), ("uniform", 3, 37), ("table", 8, 3584), ("uniform", 40, 1024)]
@@ -36,8 +37,8 @@ for kind, b, n in cases:
         x2 = t[:, :, :3].contiguous()
     x1, x2 = x1.cuda(), x2.cuda()
     dc, ac, sc, tc = run(x1, x2, 1, 10)
-    dt, at, stt, tt = run(x1, x2, 2, 10)
+    dt, at, stt, tt = run(x1, x2, alt, 10)
     ok = bool((ac == at).all()) and bool((dc == dt).all()) and bool((sc[:, :3] == stt[:, :3]).all())
     ev = lambda s: ((s[:, 4].long() & 0xffffffff) + (s[:, 5].long() << 32)).sum().item()
-    print(f"[{tag}] {kind:8s} B={b:3d} N={n:5d} cluster(cs={int(sc[0,3])}) {tc:8.1f} us | team {tt:8.1f} us | x{tc/tt:5.2f} | identical={ok} | evals {ev(sc):.3e} / {ev(stt):.3e}", flush=True)
+    print(f"[{tag}] {kind:8s} B={b:3d} N={n:5d} cluster(cs={int(sc[0,3])}) {tc:8.1f} us | path{alt} {tt:8.1f} us | x{tc/tt:5.2f} | identical={ok} | evals {ev(sc):.3e} / {ev(stt):.3e}", flush=True)
 L.pcl_emd_set_path(0)
