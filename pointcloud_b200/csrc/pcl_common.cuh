@@ -61,6 +61,12 @@ int chamfer_bwd_impl(const void *x, int x_dtype, int64_t x_bs, int64_t x_rs, con
                      const int32_t *idx_y, const float *grad_out, float g_imm_x, float g_imm_y, float *grad_x, float *grad_y,
                      cudaStream_t st);
 
+// pcl_emd_fwd_fused with a say on the worker launch of the ticket path (pcl_emd.cu)
+enum { EMD_WORKERS_AUTO = 0, EMD_WORKERS_NONE_DEDICATED = 1 };
+int emd_fwd_fused_impl(const void *xyz1, int dtype1, int64_t bs1, int64_t rs1, const void *xyz2, int dtype2, int64_t bs2, int64_t rs2, int B,
+                       int N, float eps, int iters, float *dist, int32_t *assignment, int32_t *stats, float grad_scale, float *grad_xyz1,
+                       float *sums, void *workspace, size_t workspace_bytes, void *stream, int worker_policy);
+
 static inline bool dtype_ok(int dt) { return dt == PCL_F32 || dt == PCL_F16 || dt == PCL_BF16; }
 static inline size_t align_up(size_t v, size_t a) { return (v + a - 1) / a * a; }
 

@@ -48,8 +48,11 @@ namespace {
 // second launch (emd_worker_kernel) claim them too -- they take work from the clouds that are furthest behind, which is what
 // shortens the launch: it ends with its slowest cloud -- and the bids come back as 16-byte records by list position (no scattered
 // distributed-shared-memory stores).  Iterations with few bidders keep the cluster-local warp-per-bidder path.
-template <bool PROF, bool EXPORT>
-__global__ void __launch_bounds__(EMD_THREADS, 1)
+// THREADS: 512, or 640 for clusters of at most 4 CTAs (their iterations are dominated by the lane-per-bidder scan, which gains from 20
+// warps at 80 registers: -4..9 % on early-training inputs for B >= 16; bigger clusters spend their time in the latency-bound
+// warp-per-bidder mode, where the 16-warp / 103-register build is 2-6 % faster -- profiles/r2_s2_auction_experiments.txt).
+template <bool PROF, bool EXPORT, int THREADS>
+__global__ void __launch_bounds__(THREADS, 1)
 emd_auction_kernel(Pts xyz1, Pts xyz2, int N, float eps, int iters, int flags, int pcap, int wpb_max, int items_target,
                    float *__restrict__ dist,
                    int *__restrict__ assignment, int *__restrict__ stats, long long *__restrict__ prof,
@@ -67,14 +70,15 @@ emd_auction_kernel(Pts xyz1, Pts xyz2, int N, float eps, int iters, int flags, i
     cg::cluster_group cluster = cg::this_cluster();
     const int cs = (int)cluster.num_blocks(), rank = (int)cluster.block_rank(), csl = __ffs(cs) - 1;  // cs is a power of two
     const int cloud = blockIdx.x / cs;
-    const int tid = threadIdx.x, T = EMD_THREADS, lane = tid & 31, wid = tid >> 5;
+    constexpr int NW = THREADS / 32;  // warps per CTA
+    const int tid = threadIdx.x, T = THREADS, lane = tid & 31, wid = tid >> 5;
     const size_t cold_stride = (emd_cold_bytes(N) + 255) / 256 * 256;
     const EmdSmem S = carve(smem_raw, (flags & EMD_F_COLD) ? cold_ws + (size_t)blockIdx.x * cold_stride : nullptr, N, flags, pcap);
     int *const work_ctr = S.wsum + 48;  // dynamic work-item counter of the bid phase (wsum[0..31] = warp sums)
     const int n8 = (N + 7) / 8 * 8, n32 = (N + 31) / 32 * 32, NT = n32 / TILE;
 
     // ---- init: internal (Morton) order of both clouds, tiles, auction state (emd_module.py:45-56) ----------
-    emd_setup(S, xyz1, xyz2, cloud, N, flags);
+    emd_setup<THREADS>(S, xyz1, xyz2, cloud, N, flags);
     TeamCtl *const ctl = EXPORT ? &W.ctl[cloud] : nullptr;
     unsigned char *const cl = EXPORT ? W.clouds + (size_t)cloud * W.stride : nullptr;
     if constexpr (EXPORT) {
@@ -107,12 +111,12 @@ emd_auction_kernel(Pts xyz1, Pts xyz2, int N, float eps, int iters, int flags, i
         const bool last = (t == iters - 1);
         // ---- 1. list of unassigned bidders (emd_cuda.cu:23-93), ascending, identical in every CTA -------
         if (t > 0 && (!have_list || (t & 3) == 0)) {  // prices moved in the previous iteration: refresh the per-tile upper bound of c (a stale, higher bound stays valid: with few bidders left only every fourth iteration)
-            for (int t0 = wid; t0 < NT; t0 += 4 * EMD_WARPS) {  // four independent tiles per trip
+            for (int t0 = wid; t0 < NT; t0 += 4 * NW) {  // four independent tiles per trip
                 // warp maximum with one REDUX on an order-preserving integer image of the float (c may be negative: padding)
                 int b[4];
 #pragma unroll
                 for (int i = 0; i < 4; i++) {
-                    const int tl = min(t0 + i * EMD_WARPS, NT - 1);
+                    const int tl = min(t0 + i * NW, NT - 1);
                     b[i] = __float_as_int(S.tgt[tl * TILE + lane].w);
                     b[i] ^= (b[i] >> 31) & 0x7fffffff;
                 }
@@ -120,7 +124,7 @@ emd_auction_kernel(Pts xyz1, Pts xyz2, int N, float eps, int iters, int flags, i
                 for (int i = 0; i < 4; i++) b[i] = __reduce_max_sync(0xffffffffu, b[i]);
 #pragma unroll
                 for (int i = 0; i < 4; i++) {
-                    const int tl = t0 + i * EMD_WARPS;
+                    const int tl = t0 + i * NW;
                     b[i] ^= (b[i] >> 31) & 0x7fffffff;
                     if (lane == 0 && tl < NT) S.tlo[tl].w = __int_as_float(b[i]);
                 }
@@ -132,7 +136,7 @@ emd_auction_kernel(Pts xyz1, Pts xyz2, int N, float eps, int iters, int flags, i
             // while it committed the bids -- identical in every CTA, and the dealing does not need it sorted.
             U = S.wsum[40];
             if (U == 0) break;
-            if (tid == 0) *work_ctr = EMD_WARPS;
+            if (tid == 0) *work_ctr = NW;
         } else {
         unsigned fl = 0;
         {
@@ -160,13 +164,13 @@ emd_auction_kernel(Pts xyz1, Pts xyz2, int N, float eps, int iters, int flags, i
         __syncthreads();
         int wbase = 0;
 #pragma unroll
-        for (int w = 0; w < EMD_WARPS; w++) {
+        for (int w = 0; w < NW; w++) {
             const int v = S.wsum[w];
             if (w < wid) wbase += v;
             U += v;
         }
         if (U == 0) break;  // uniform across the cluster: replicas are identical
-        if (tid == 0) *work_ctr = EMD_WARPS;  // the first work item of warp w is item w (no atomic on the critical path), the rest is dynamic
+        if (tid == 0) *work_ctr = NW;  // the first work item of warp w is item w (no atomic on the critical path), the rest is dynamic
         {
             int pos = wbase + incl - cnt;
             const int base = tid * E;
@@ -241,7 +245,7 @@ emd_auction_kernel(Pts xyz1, Pts xyz2, int N, float eps, int iters, int flags, i
         if constexpr (EXPORT) {
             if (rank == 0 && W.nworkers > 0) {  // progress of this cloud out, progress of all clouds in (consumed at the end of the bid phase)
                 if (tid == 0) *reinterpret_cast<volatile int *>(&ctl->prog) = wpb ? iters : t;
-                if (wid == EMD_WARPS - 1)
+                if (wid == NW - 1)
                     for (int c = lane; c < (int)gridDim.x / cs; c += 32) prog_sum += (int)ld_relaxed_u32(reinterpret_cast<const unsigned *>(&W.ctl[c].prog));
             }
             if (rank == 0 && tid == 0 && !told_workers && wpb) atomicAdd(W.finished, 1u);  // U never grows: no exported iteration will follow
@@ -514,7 +518,7 @@ emd_auction_kernel(Pts xyz1, Pts xyz2, int N, float eps, int iters, int flags, i
         }
         PCL_TICK(7)
         if constexpr (EXPORT) {
-            if (!wpb && rank == 0 && wid == EMD_WARPS - 1 && W.nworkers > 0) {  // export share of the NEXT iteration from the mean lag (in iterations)
+            if (!wpb && rank == 0 && wid == NW - 1 && W.nworkers > 0) {  // export share of the NEXT iteration from the mean lag (in iterations)
                 const int nb = (int)gridDim.x / cs;
                 const float lag = (float)__reduce_add_sync(0xffffffffu, prog_sum) / (float)nb - (float)t;
                 int pct = 0;
@@ -542,7 +546,7 @@ emd_auction_kernel(Pts xyz1, Pts xyz2, int N, float eps, int iters, int flags, i
                     __syncthreads();
                     const int task = S.wsum[56];
                     if (task < 0) break;
-                    team_run_task(S, NT, eps, th, task, g_brec, g_jp, g_pub, my_evals);
+                    team_run_task<THREADS>(S, NT, eps, th, task, g_brec, g_jp, g_pub, my_evals);
                     __threadfence();
                     __syncthreads();
                     if (tid == 0) { __threadfence(); atomicAdd(&ctl->done, 1u); }
@@ -619,8 +623,10 @@ emd_auction_kernel(Pts xyz1, Pts xyz2, int N, float eps, int iters, int flags, i
                     reinterpret_cast<float4 *>(cl + W.o_tgt)[o].w = cnew;
                 }
             }
-            S.maxinc[o] = -1e9f;
-            S.maxidx[o] = -1;
+            if (!last) {  // (in the last iteration every bidder commits: resetting here would hide the winner from the statistics of a later thread)
+                S.maxinc[o] = -1e9f;
+                S.maxidx[o] = -1;
+            }
         }
         have_list = (U <= 32);
         if (have_list && wid == 0) {  // losers in list order, then evicted owners in list order: ballot compaction inside warp 0
@@ -677,7 +683,7 @@ emd_auction_kernel(Pts xyz1, Pts xyz2, int N, float eps, int iters, int flags, i
         __syncthreads();
         if (tid == 0) {
             double b = 0.0;
-            for (int w = 0; w < EMD_WARPS; w++) b += red[w];
+            for (int w = 0; w < NW; w++) b += red[w];
             part[blockIdx.x] = b;
             __threadfence();
             S.wsum[41] = (atomicAdd(ticket, 1u) == gridDim.x - 1) ? 1 : 0;
@@ -714,13 +720,21 @@ emd_auction_kernel(Pts xyz1, Pts xyz2, int N, float eps, int iters, int flags, i
         cluster.sync();
         if (rank == 0 && tid == 0) {
             int e = 0;
-            for (int w = 0; w < EMD_WARPS; w++) e += S.wsum[w];
+            for (int w = 0; w < NW; w++) e += S.wsum[w];
             int *st = stats + (size_t)cloud * 8;
             st[0] = (int)sum_u; st[1] = iters_run; st[2] = e; st[3] = cs;
             unsigned long long ce = *S.evals;
             if constexpr (EXPORT) ce += atomicAdd(&ctl->evals, 0ull);  // evaluations the workers executed for this cloud
             st[4] = (int)(ce & 0xffffffffull); st[5] = (int)(ce >> 32);
             st[6] = flags; st[7] = NT;
+        }
+    }
+    if constexpr (EXPORT) {
+        // This cloud is done: its CTAs serve the tickets of the clouds that are still running (the launch ends with the slowest cloud,
+        // and by now that cloud exports a large share of its iterations) until every cloud is past its exported iterations.
+        if (W.nworkers > 0) {
+            __syncthreads();
+            team_worker<THREADS>(S, W, (int)gridDim.x / cs, N, eps, (int)blockIdx.x, 0, nullptr);
         }
     }
 }
@@ -858,7 +872,7 @@ int pick_cluster_impl(int B, int N, int sm_count, size_t smem, cudaStream_t st, 
         at[0].val.clusterDim.x = cs; at[0].val.clusterDim.y = 1; at[0].val.clusterDim.z = 1;
         cfg.attrs = at; cfg.numAttrs = 1;
         int ncl = 0;
-        cudaError_t e = cudaOccupancyMaxActiveClusters(&ncl, emd_auction_kernel<false, false>, &cfg);
+        cudaError_t e = cudaOccupancyMaxActiveClusters(&ncl, emd_auction_kernel<false, false, EMD_THREADS>, &cfg);
         if (e == cudaSuccess && ncl >= B) break;
         (void)cudaGetLastError();
         cs >>= 1;
@@ -869,7 +883,7 @@ int pick_cluster_impl(int B, int N, int sm_count, size_t smem, cudaStream_t st, 
 }
 
 // development aids, read once per process: PCL_EMD_NO_SORT, PCL_EMD_PCAP, PCL_EMD_WPB, PCL_EMD_ITEMS, PCL_EMD_PROFILE, PCL_EMD_TEAM*
-struct EmdEnv { bool no_sort, profile; int pcap, wpb, items, cs, path, team_tasks, team_local, team_wpb, team_grid, team_idle, team_export, team_lagmin, team_slope; };
+struct EmdEnv { bool no_sort, profile; int pcap, wpb, items, cs, threads, path, team_tasks, team_local, team_wpb, team_grid, team_idle, team_export, team_lagmin, team_slope; };
 const EmdEnv &emd_env() {
     static const EmdEnv e = [] {
         EmdEnv v;
@@ -880,6 +894,7 @@ const EmdEnv &emd_env() {
         v.wpb = (s = getenv("PCL_EMD_WPB")) ? atoi(s) : -1;
         v.items = (s = getenv("PCL_EMD_ITEMS")) ? atoi(s) : 0;
         v.cs = (s = getenv("PCL_EMD_CS")) ? atoi(s) : 0;
+        v.threads = (s = getenv("PCL_EMD_THREADS")) ? atoi(s) : 0;  // 512: never the 640-thread build
         v.path = (s = getenv("PCL_EMD_PATH")) ? atoi(s) : 0;               // PCL_EMD_PATH_* of include/pcl.h when pcl_emd_set_path says AUTO
         v.team_export = (s = getenv("PCL_EMD_TEAM_EXPORT")) ? atoi(s) : -1;  // percent of a lane-per-bidder iteration's bidders exported as tickets
         v.team_lagmin = (s = getenv("PCL_EMD_TEAM_LAGMIN")) ? atoi(s) : -1;  // quarter iterations behind the mean from which a cloud exports
@@ -978,6 +993,15 @@ extern "C" int pcl_emd_fwd_fused(const void *xyz1, int dtype1, int64_t bs1, int6
                                  int64_t bs2, int64_t rs2, int B, int N, float eps, int iters, float *dist,
                                  int32_t *assignment, int32_t *stats, float grad_scale, float *grad_xyz1, float *sums,
                                  void *workspace, size_t workspace_bytes, void *stream) {
+    return pcl::emd_fwd_fused_impl(xyz1, dtype1, bs1, rs1, xyz2, dtype2, bs2, rs2, B, N, eps, iters, dist, assignment, stats, grad_scale, grad_xyz1,
+                                   sums, workspace, workspace_bytes, stream, EMD_WORKERS_AUTO);
+}
+
+// worker_policy EMD_WORKERS_NONE_DEDICATED: the caller runs other kernels next to the auction (the composite step's Chamfer on the SMs the
+// clusters leave free), so no dedicated worker CTAs are launched; finished clusters still help the slow clouds.
+int pcl::emd_fwd_fused_impl(const void *xyz1, int dtype1, int64_t bs1, int64_t rs1, const void *xyz2, int dtype2, int64_t bs2, int64_t rs2, int B,
+                            int N, float eps, int iters, float *dist, int32_t *assignment, int32_t *stats, float grad_scale, float *grad_xyz1,
+                            float *sums, void *workspace, size_t workspace_bytes, void *stream, int worker_policy) {
     int rc = emd_check(xyz1, dtype1, xyz2, dtype2, B, N, "emd_fwd");
     if (rc) return rc;
     if (iters < 0) { set_error("emd_fwd: iters=%d", iters); return PCL_E_ARG; }
@@ -1005,27 +1029,29 @@ extern "C" int pcl_emd_fwd_fused(const void *xyz1, int dtype1, int64_t bs1, int6
     if (N <= EMD_SMEM_ONLY_N && emd_smem_bytes(N, flags | EMD_F_X1) <= (size_t)di.max_smem_optin) flags |= EMD_F_X1;
     const EmdEnv &env = emd_env();
     if (env.no_sort) flags &= ~EMD_F_SORT;  // development aid: natural order (no spatial pruning benefit)
-    int pcap = 2 * EMD_THREADS;  // room for 32 work items with partials; fall back to 16 when shared memory is tight
-    if (env.pcap > 0) pcap = env.pcap;  // development aid: work items with partials
-    while (pcap > EMD_THREADS && emd_smem_bytes(N, flags, pcap) > (size_t)di.max_smem_optin) pcap -= EMD_THREADS;
-    const size_t smem = emd_smem_bytes(N, flags, pcap);
-    int wpb_max = EMD_WPB_MAX;
-    if (env.wpb >= 0) wpb_max = env.wpb;  // development aid
-    int items_target = 2 * EMD_WARPS;  // work items per CTA and iteration in the lane-per-bidder mode (dynamic queue; swept 8..128 on config 2)
-    if (env.items > 0) items_target = env.items;  // development aid
-    if (smem > (size_t)di.max_smem_optin) { set_error("emd_fwd: N=%d needs %zu B shared memory (> %d)", N, smem, di.max_smem_optin); return PCL_E_UNSUPPORTED; }
     static thread_local int attr_dev = -1;
     int dev = 0;
     PCL_CUDA(cudaGetDevice(&dev));
     if (attr_dev != dev) {
-        const void *kernels[4] = {(const void *)emd_auction_kernel<false, false>, (const void *)emd_auction_kernel<true, false>,
-                                  (const void *)emd_auction_kernel<false, true>, (const void *)emd_auction_kernel<true, true>};
+        const void *kernels[6] = {(const void *)emd_auction_kernel<false, false, EMD_THREADS>, (const void *)emd_auction_kernel<true, false, EMD_THREADS>,
+                                  (const void *)emd_auction_kernel<false, true, EMD_THREADS>, (const void *)emd_auction_kernel<true, true, EMD_THREADS>,
+                                  (const void *)emd_auction_kernel<false, false, EMD_THREADS_WIDE>, (const void *)emd_auction_kernel<false, true, EMD_THREADS_WIDE>};
         for (const void *k : kernels) {
             PCL_CUDA(cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, di.max_smem_optin));
             PCL_CUDA(cudaFuncSetAttribute(k, cudaFuncAttributeNonPortableClusterSizeAllowed, 1));
         }
         attr_dev = dev;
     }
+    // cluster size first (with the 512-thread configuration), then the CTA size that goes with it
+    int pcap = 2 * EMD_THREADS;  // room for 32 work items with partials; fall back to 16 when shared memory is tight
+    if (env.pcap > 0) pcap = env.pcap;  // development aid: work items with partials
+    while (pcap > EMD_THREADS && emd_smem_bytes(N, flags, pcap) > (size_t)di.max_smem_optin) pcap -= EMD_THREADS;
+    size_t smem = emd_smem_bytes(N, flags, pcap);
+    if (smem > (size_t)di.max_smem_optin) { set_error("emd_fwd: N=%d needs %zu B shared memory (> %d)", N, smem, di.max_smem_optin); return PCL_E_UNSUPPORTED; }
+    const int cs = pick_cluster(B, N, di.sm_count, smem, st);
+    const int pcap512 = pcap;  // the team kernel always runs 512 threads
+    const size_t smem512 = smem;
+    int threads = EMD_THREADS;
     unsigned *ticket = sums ? (unsigned *)workspace : nullptr;
     double *part = sums ? (double *)((unsigned char *)workspace + 256) : nullptr;
     if (sums) PCL_CUDA(cudaMemsetAsync(ticket, 0, sizeof(unsigned), st));
@@ -1042,17 +1068,27 @@ extern "C" int pcl_emd_fwd_fused(const void *xyz1, int dtype1, int64_t bs1, int6
         set_error("emd_fwd: the team / ticket paths need N <= %d, B < %d and a workspace of pcl_emd_workspace_bytes", EMD_SMEM_ONLY_N, di.sm_count);
         return PCL_E_UNSUPPORTED;
     }
-    const int cs = pick_cluster(B, N, di.sm_count, smem, st);
     if (path == PCL_EMD_PATH_AUTO) {
         // Measured on B200 over B = 1..128, N = 1024 / 2048 / 3584, early- and late-training inputs (profiles/r2_s2_path_sweep*.txt), judged
-        // on the sum of both regimes: big clouds are throughput-bound -> owner + workers; small clusters (many clouds) or many free SMs
-        // -> clusters + workers on the free SMs; otherwise (B <= 12, and the B = 32 launch of the benchmark, which leaves only 20 SMs)
-        // the plain cluster kernel, whose distributed-shared-memory exchange has the lowest latency per iteration.
-        const int free_sms = di.sm_count - B * cs;
+        // on the sum of both regimes: big clouds are throughput-bound -> owner + workers; many clouds in small clusters (B >= 38: clusters
+        // of 2 or 1) -> clusters + workers on the free SMs + finished clusters helping the slow ones (-10..20 %); otherwise (and for the
+        // B = 32 launch of the benchmark) the plain cluster kernel, whose distributed-shared-memory exchange has the lowest latency per
+        // iteration.
         path = PCL_EMD_PATH_CLUSTER;
         if (can && N >= 3072 && B >= 8) path = PCL_EMD_PATH_TEAM;
-        else if (can && N >= 1536 && B >= 8 && (cs <= 2 || (cs == 4 && free_sms >= 48))) path = PCL_EMD_PATH_TICKETS;
+        else if (can && N >= 1536 && cs <= 2) path = PCL_EMD_PATH_TICKETS;  // (clusters of 4 with many free SMs gain 1-3 % on the mix: not worth the second launch)
     }
+    // CTA size: 640 threads where the lane-per-bidder scan dominates (plain clusters of <= 4 CTAs, ticket path with clusters of <= 2)
+    if (!(flags & EMD_F_COLD) && env.threads != 512 && !env.profile && env.pcap <= 0 &&
+        ((path == PCL_EMD_PATH_CLUSTER && cs <= 4) || (path == PCL_EMD_PATH_TICKETS && cs <= 2))) {
+        const int pc = 2 * EMD_THREADS_WIDE;
+        if (emd_smem_bytes(N, flags, pc) <= (size_t)di.max_smem_optin) { threads = EMD_THREADS_WIDE; pcap = pc; smem = emd_smem_bytes(N, flags, pcap); }
+    }
+    const int warps = threads / 32;
+    int wpb_max = 6 * warps;  // at most this many bidders per CTA: warp-per-bidder scan (swept on config 2: 48..128 at 16 warps)
+    if (env.wpb >= 0) wpb_max = env.wpb;  // development aid
+    int items_target = 2 * warps;  // work items per CTA and iteration in the lane-per-bidder mode (dynamic queue; swept 8..128 on config 2)
+    if (env.items > 0) items_target = env.items;  // development aid
     void *team_ws = can ? (unsigned char *)workspace + (all_bytes - team_bytes) : nullptr;
     long long *prof_team = env.profile && workspace ? (long long *)((unsigned char *)workspace + emd_fused_bytes(B)) : nullptr;  // 16 int64 per CTA, <= 256 CTAs
     if (path == PCL_EMD_PATH_TEAM) {
@@ -1061,11 +1097,11 @@ extern "C" int pcl_emd_fwd_fused(const void *xyz1, int dtype1, int64_t bs1, int6
         const int tasks_target = env.team_tasks > 0 ? env.team_tasks : (3 * grid / B + 1) / 2;  // ~1.5 tasks per CTA that can work on a cloud
         const int local_max = env.team_local >= 0 ? env.team_local : 32;
         const int team_wpb = env.team_wpb >= 0 ? env.team_wpb : 4 * EMD_WPB_MAX;
-        return emd_team_launch(p1, p2, B, N, eps, iters, flags, pcap, team_wpb, tasks_target, local_max, grid, smem, dist, (int *)assignment,
+        return emd_team_launch(p1, p2, B, N, eps, iters, flags, pcap512, team_wpb, tasks_target, local_max, grid, smem512, dist, (int *)assignment,
                                (int *)stats, team_ws, grad_scale, grad_xyz1, part, ticket, sums, prof_team, st);
     }
     cudaLaunchConfig_t cfg = {};
-    cfg.gridDim = dim3(B * cs); cfg.blockDim = dim3(EMD_THREADS); cfg.dynamicSmemBytes = smem; cfg.stream = st;
+    cfg.gridDim = dim3(B * cs); cfg.blockDim = dim3(threads); cfg.dynamicSmemBytes = smem; cfg.stream = st;
     cudaLaunchAttribute at[1];
     at[0].id = cudaLaunchAttributeClusterDimension;
     at[0].val.clusterDim.x = cs; at[0].val.clusterDim.y = 1; at[0].val.clusterDim.z = 1;
@@ -1074,14 +1110,16 @@ extern "C" int pcl_emd_fwd_fused(const void *xyz1, int dtype1, int64_t bs1, int6
     const size_t rest_bytes = workspace_bytes > emd_fused_bytes(B) ? workspace_bytes - emd_fused_bytes(B) : 0;
     const bool prof_ok = env.profile && !(flags & EMD_F_COLD) && rest && rest_bytes >= ((size_t)B * cs * 16 + 512) * sizeof(long long);
     if (path == PCL_EMD_PATH_TICKETS) {
-        int nworkers = env.team_grid > 0 ? env.team_grid - B * cs : di.sm_count - B * cs;  // the SMs the clusters leave free
-        if (nworkers < 0 || env.team_grid == -1) nworkers = 0;
-        const int tasks_target = env.team_tasks > 0 ? env.team_tasks : max(4, (2 * nworkers + B - 1) / B);  // exported tickets per cloud and iteration: ~2 per worker that serves the cloud, at least 4 (swept 2..8 at B=32)
+        // dedicated worker CTAs (a second launch) on the SMs the clusters leave free; besides them, the CTAs of every cluster whose
+        // auction is over serve tickets until the last cloud is done (W.nworkers > 0 switches the export machinery on)
+        int nworkers = env.team_grid > 0 ? env.team_grid - B * cs : di.sm_count - B * cs;
+        if (nworkers < 0 || env.team_grid == -1 || worker_policy == EMD_WORKERS_NONE_DEDICATED) nworkers = 0;
+        const int tasks_target = env.team_tasks > 0 ? env.team_tasks : max(4, (2 * (nworkers > 0 ? nworkers : di.sm_count - B * cs) + B - 1) / B);  // exported tickets per cloud and iteration: ~2 per worker that serves the cloud, at least 4 (swept 2..8 at B=32)
                 int export_pct = env.team_export >= 0 ? env.team_export : 50;  // upper limit of the exported share (percent)
         if (export_pct > 60) export_pct = 60;
         const int lag_min_q = env.team_lagmin >= 0 ? env.team_lagmin : 4;   // a cloud exports when it lags >= this many quarter iterations behind the mean
         const int lag_slope = env.team_slope >= 0 ? env.team_slope : 5;     // exported percent = 20 + slope * lag
-        const TeamWs W = team_ws_make(team_ws, B, N, nworkers);
+        const TeamWs W = team_ws_make(team_ws, B, N, nworkers > 0 ? nworkers : 1);
         PCL_CUDA(cudaMemsetAsync(team_ws, 0, team_ctl_bytes(B), st));
         WorkerStream *ws = nullptr;
         if (nworkers > 0) {
@@ -1090,9 +1128,13 @@ extern "C" int pcl_emd_fwd_fused(const void *xyz1, int dtype1, int64_t bs1, int6
             PCL_CUDA(cudaEventRecord(ws->fork, st));  // the workers need the zeroed control block, nothing else
         }
         if (prof_ok) {
-            PCL_CUDA(cudaLaunchKernelEx(&cfg, emd_auction_kernel<true, true>, p1, p2, N, eps, iters, flags, pcap, wpb_max, items_target, dist, (int *)assignment, (int *)stats, (long long *)rest, (unsigned char *)nullptr, grad_scale, grad_xyz1, part, ticket, sums, W, tasks_target, export_pct, lag_min_q, lag_slope));
+            PCL_CUDA(cudaLaunchKernelEx(&cfg, emd_auction_kernel<true, true, EMD_THREADS>, p1, p2, N, eps, iters, flags, pcap, wpb_max, items_target, dist, (int *)assignment, (int *)stats, (long long *)rest, (unsigned char *)nullptr, grad_scale, grad_xyz1, part, ticket, sums, W, tasks_target, export_pct, lag_min_q, lag_slope));
         } else {
-            PCL_CUDA(cudaLaunchKernelEx(&cfg, emd_auction_kernel<false, true>, p1, p2, N, eps, iters, flags, pcap, wpb_max, items_target, dist, (int *)assignment, (int *)stats, (long long *)nullptr, (unsigned char *)nullptr, grad_scale, grad_xyz1, part, ticket, sums, W, tasks_target, export_pct, lag_min_q, lag_slope));
+            if (threads == EMD_THREADS_WIDE) {
+                PCL_CUDA(cudaLaunchKernelEx(&cfg, emd_auction_kernel<false, true, EMD_THREADS_WIDE>, p1, p2, N, eps, iters, flags, pcap, wpb_max, items_target, dist, (int *)assignment, (int *)stats, (long long *)nullptr, (unsigned char *)nullptr, grad_scale, grad_xyz1, part, ticket, sums, W, tasks_target, export_pct, lag_min_q, lag_slope));
+            } else {
+                PCL_CUDA(cudaLaunchKernelEx(&cfg, emd_auction_kernel<false, true, EMD_THREADS>, p1, p2, N, eps, iters, flags, pcap, wpb_max, items_target, dist, (int *)assignment, (int *)stats, (long long *)nullptr, (unsigned char *)nullptr, grad_scale, grad_xyz1, part, ticket, sums, W, tasks_target, export_pct, lag_min_q, lag_slope));
+            }
         }
         if (nworkers > 0) {
             // Launched AFTER the clusters (they must not find their SMs taken) on a stream of their own; a worker leaves when every
@@ -1109,9 +1151,13 @@ extern "C" int pcl_emd_fwd_fused(const void *xyz1, int dtype1, int64_t bs1, int6
     const TeamWs W0 = {};
     // development aid: PCL_EMD_PROFILE=1 makes the workspace receive per-phase clock totals (B*cs*16 int64)
     if (prof_ok) {
-        PCL_CUDA(cudaLaunchKernelEx(&cfg, emd_auction_kernel<true, false>, p1, p2, N, eps, iters, flags, pcap, wpb_max, items_target, dist, (int *)assignment, (int *)stats, (long long *)rest, (unsigned char *)nullptr, grad_scale, grad_xyz1, part, ticket, sums, W0, 0, 0, 0, 0));
+        PCL_CUDA(cudaLaunchKernelEx(&cfg, emd_auction_kernel<true, false, EMD_THREADS>, p1, p2, N, eps, iters, flags, pcap, wpb_max, items_target, dist, (int *)assignment, (int *)stats, (long long *)rest, (unsigned char *)nullptr, grad_scale, grad_xyz1, part, ticket, sums, W0, 0, 0, 0, 0));
     } else {
-        PCL_CUDA(cudaLaunchKernelEx(&cfg, emd_auction_kernel<false, false>, p1, p2, N, eps, iters, flags, pcap, wpb_max, items_target, dist, (int *)assignment, (int *)stats, (long long *)nullptr, (unsigned char *)((flags & EMD_F_COLD) ? rest : nullptr), grad_scale, grad_xyz1, part, ticket, sums, W0, 0, 0, 0, 0));
+        if (threads == EMD_THREADS_WIDE) {
+            PCL_CUDA(cudaLaunchKernelEx(&cfg, emd_auction_kernel<false, false, EMD_THREADS_WIDE>, p1, p2, N, eps, iters, flags, pcap, wpb_max, items_target, dist, (int *)assignment, (int *)stats, (long long *)nullptr, (unsigned char *)((flags & EMD_F_COLD) ? rest : nullptr), grad_scale, grad_xyz1, part, ticket, sums, W0, 0, 0, 0, 0));
+        } else {
+            PCL_CUDA(cudaLaunchKernelEx(&cfg, emd_auction_kernel<false, false, EMD_THREADS>, p1, p2, N, eps, iters, flags, pcap, wpb_max, items_target, dist, (int *)assignment, (int *)stats, (long long *)nullptr, (unsigned char *)((flags & EMD_F_COLD) ? rest : nullptr), grad_scale, grad_xyz1, part, ticket, sums, W0, 0, 0, 0, 0));
+        }
     }
     return PCL_OK;
 }

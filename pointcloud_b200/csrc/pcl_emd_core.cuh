@@ -26,6 +26,10 @@ namespace {
 #endif
 constexpr int EMD_THREADS = PCL_EMD_THREADS;
 constexpr int EMD_WARPS = EMD_THREADS / 32;
+#ifndef PCL_EMD_THREADS_WIDE
+#define PCL_EMD_THREADS_WIDE 640
+#endif
+constexpr int EMD_THREADS_WIDE = PCL_EMD_THREADS_WIDE;  // the cluster kernel's second build: 20 warps at 80 registers for clusters of <= 4 CTAs
 constexpr int EMD_MAX_N = 8192;      // EMD_SMEM_ONLY_N+1..8192: the cold half of the state lives in a per-CTA global-memory region (L2)
 constexpr int EMD_SMEM_ONLY_N = 3584;  // up to here the whole auction state (58 B/point + 9 KB) fits into 227 KB of shared memory
 constexpr int TILE = 32;  // targets per spatial tile (one bounding box per tile)
@@ -228,8 +232,9 @@ __device__ __forceinline__ Top2 top2_init(float tm) {
 
 // Set-up of one CTA's replica (emd_module.py:45-56 + the internal order): both clouds in Morton order, target tiles with their
 // boxes, empty auction state.  Ends WITHOUT a barrier: the caller synchronises (cluster or block) before anyone reads the state.
+template <int THREADS>
 __device__ __forceinline__ void emd_setup(const EmdSmem &S, const Pts &xyz1, const Pts &xyz2, int cloud, int N, int flags) {
-    const int tid = threadIdx.x, T = EMD_THREADS, lane = tid & 31, wid = tid >> 5;
+    const int tid = threadIdx.x, T = THREADS, lane = tid & 31, wid = tid >> 5;
     const int n8 = (N + 7) / 8 * 8, n32 = (N + 31) / 32 * 32, NT = n32 / TILE;
     if (tid == 0) *S.evals = 0ull;
     if (flags & EMD_F_SORT) {
@@ -253,9 +258,9 @@ __device__ __forceinline__ void emd_setup(const EmdSmem &S, const Pts &xyz1, con
             for (int k = tid; k < N; k += T) rnk[k] = (unsigned short)atomicAdd(&hist[H((int)(morton18(ld_xyz(src, cloud, k)) >> cshift))], 1);
             __syncthreads();
             {   // exclusive prefix sum over the cells: ncell / T consecutive cells per thread + block scan
-                const int cpt = ncell / EMD_THREADS;
+                const int cpt = (ncell + THREADS - 1) / THREADS;  // (exact for 512 threads; other CTA sizes leave the last threads idle)
                 int sum = 0;
-                for (int i = 0; i < cpt; i++) sum += hist[H(tid * cpt + i)];
+                for (int i = 0; i < cpt; i++) sum += (tid * cpt + i < ncell) ? hist[H(tid * cpt + i)] : 0;
                 int incl2 = sum;
 #pragma unroll
                 for (int o = 1; o < 32; o <<= 1) {
@@ -266,7 +271,9 @@ __device__ __forceinline__ void emd_setup(const EmdSmem &S, const Pts &xyz1, con
                 __syncthreads();
                 int base = incl2 - sum;
                 for (int w = 0; w < wid; w++) base += S.wsum[w];
-                for (int i = 0; i < cpt; i++) { const int v = hist[H(tid * cpt + i)]; hist[H(tid * cpt + i)] = base; base += v; }
+                for (int i = 0; i < cpt; i++) {
+                    if (tid * cpt + i < ncell) { const int v = hist[H(tid * cpt + i)]; hist[H(tid * cpt + i)] = base; base += v; }
+                }
             }
             __syncthreads();
             // scatter (fine key | original index) in arrival order, then rank every point among its cell mates by that
@@ -309,7 +316,7 @@ __device__ __forceinline__ void emd_setup(const EmdSmem &S, const Pts &xyz1, con
         S.last34[j] = NOLAST;
     }
     __syncthreads();
-    for (int t = wid; t < NT; t += EMD_WARPS) {  // tile boxes
+    for (int t = wid; t < NT; t += THREADS / 32) {  // tile boxes
         const int k = t * TILE + lane;
         const float4 p = S.tgt[k];
         const bool ok = k < N;

@@ -78,10 +78,10 @@ __device__ __forceinline__ void st_release_u64(unsigned long long *p, unsigned l
 
 // 16-byte copies global (L2, never the possibly stale L1) -> shared
 __device__ __forceinline__ void copy16_in(void *dst, const void *src, int n16) {
-    for (int i = threadIdx.x; i < n16; i += EMD_THREADS) reinterpret_cast<uint4 *>(dst)[i] = __ldcg(reinterpret_cast<const uint4 *>(src) + i);
+    for (int i = threadIdx.x; i < n16; i += (int)blockDim.x) reinterpret_cast<uint4 *>(dst)[i] = __ldcg(reinterpret_cast<const uint4 *>(src) + i);
 }
 __device__ __forceinline__ void copy16_out(void *dst, const void *src, int n16) {
-    for (int i = threadIdx.x; i < n16; i += EMD_THREADS) reinterpret_cast<uint4 *>(dst)[i] = reinterpret_cast<const uint4 *>(src)[i];
+    for (int i = threadIdx.x; i < n16; i += (int)blockDim.x) reinterpret_cast<uint4 *>(dst)[i] = reinterpret_cast<const uint4 *>(src)[i];
 }
 
 // One bidder scanned by one warp, one lane per target of a tile (the warp-per-bidder mode of pcl_emd.cu): 32 boxes per ballot, up to
@@ -208,6 +208,7 @@ __device__ __forceinline__ TaskHdr task_policy(int U, bool wpb, int tasks_target
 // neighbouring bidders, every group scanned in KS tile slices (TB/32*KS work items for the 16 warps, dynamic queue, slice partials
 // merged by the tree of pcl_emd.cu == emd_cuda.cu:165-173).  mode 1: warp-per-bidder -- one bidder per warp at a time.
 // Bids go to pub[list position] = {object | second << 16, increment bits, third | fourth << 16, 0}.
+template <int THREADS>
 __device__ __forceinline__ void team_run_task(const EmdSmem &S, int NT, float eps, const TaskHdr &h, int task,
                                               const float4 *__restrict__ brec, const unsigned short *__restrict__ bjp,
                                               uint4 *__restrict__ pub, unsigned long long &my_evals) {
@@ -215,7 +216,7 @@ __device__ __forceinline__ void team_run_task(const EmdSmem &S, int NT, float ep
     int *const work_ctr = S.wsum + 48;
     const int b0 = task * h.TB;                            // first list position of the task
     const int nb = min(h.TB, h.U - b0);                    // bidders of the task
-    if (tid == 0) *work_ctr = EMD_WARPS;
+    if (tid == 0) *work_ctr = THREADS / 32;
     __syncthreads();
     if (h.mode == 1) {
         for (int i = wid;;) {
@@ -269,7 +270,7 @@ __device__ __forceinline__ void team_run_task(const EmdSmem &S, int NT, float ep
         while (span < KS) span <<= 1;
         for (int st = span >> 1; st >= 1; st >>= 1) {
             const int rows = min(st, KS - st);  // slices c in [0, rows) absorb slice c + st
-            for (int idx = tid; idx < rows * nb; idx += EMD_THREADS) {
+            for (int idx = tid; idx < rows * nb; idx += THREADS) {
                 const int c = idx / nb, b = idx - c * nb;
                 const int me = c * GS + b, ot = (c + st) * GS + b;
                 float best = S.pbest[me], better = S.pbetter[me];
@@ -299,7 +300,7 @@ __device__ __forceinline__ void team_run_task(const EmdSmem &S, int NT, float ep
             }
             __syncthreads();
         }
-        for (int b = tid; b < nb; b += EMD_THREADS)
+        for (int b = tid; b < nb; b += THREADS)
             pub[b0 + b] = make_uint4(S.pbi[b], __float_as_uint(__fadd_rn(__fsub_rn(S.pbest[b], S.pbetter[b]), eps)), S.pbi34[b], 0u);
     }
 }
@@ -308,6 +309,7 @@ __device__ __forceinline__ void team_run_task(const EmdSmem &S, int NT, float ep
 #define PCL_SPIN_LIMIT (1u << 25)
 
 // widx: index of this worker (home cloud = widx mod B); idle_limit: leave after this many cycles without a ticket (0: never)
+template <int THREADS>
 __device__ void team_worker(const EmdSmem &S, const TeamWs &W, int B, int N, float eps, int widx, long long idle_limit, long long *prof) {
     const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
     const int n8 = (N + 7) / 8 * 8, n32 = (N + 31) / 32 * 32, NT = n32 / TILE;
@@ -388,11 +390,11 @@ __device__ void team_worker(const EmdSmem &S, const TeamWs &W, int B, int N, flo
             const int c_tgt = n32, c_pf = n8 / 4, c_box = 2 * NT, c_tp = (c != cached_c && S.tperm) ? n8 / 8 : 0;
             const int total = c_tgt + c_pf + c_box + c_tp;
             constexpr int PER = 8;  // 16 B x 8 x 512 threads = 64 KB per round
-            for (int base = 0; base < total; base += PER * EMD_THREADS) {
+            for (int base = 0; base < total; base += PER * THREADS) {
                 uint4 v[PER];
 #pragma unroll
                 for (int i = 0; i < PER; i++) {
-                    const int e = base + i * EMD_THREADS + tid;
+                    const int e = base + i * THREADS + tid;
                     const unsigned char *src = nullptr;
                     if (e < c_tgt) src = cl + W.o_tgt + (size_t)e * 16;
                     else if (e < c_tgt + c_pf) src = cl + W.o_pf + (size_t)(e - c_tgt) * 16;
@@ -402,7 +404,7 @@ __device__ void team_worker(const EmdSmem &S, const TeamWs &W, int B, int N, flo
                 }
 #pragma unroll
                 for (int i = 0; i < PER; i++) {
-                    const int e = base + i * EMD_THREADS + tid;
+                    const int e = base + i * THREADS + tid;
                     unsigned char *dst = nullptr;
                     if (e < c_tgt) dst = reinterpret_cast<unsigned char *>(S.tgt) + (size_t)e * 16;
                     else if (e < c_tgt + c_pf) dst = reinterpret_cast<unsigned char *>(S.pf) + (size_t)(e - c_tgt) * 16;
@@ -418,7 +420,7 @@ __device__ void team_worker(const EmdSmem &S, const TeamWs &W, int B, int N, flo
         pt[4]++;
         PCL_WTICK(1)
         // (team_run_task starts with a block barrier: the copies are visible to every warp before the first scan)
-        team_run_task(S, NT, eps, h, (int)ticket - base, reinterpret_cast<const float4 *>(cl + W.o_brec),
+        team_run_task<THREADS>(S, NT, eps, h, (int)ticket - base, reinterpret_cast<const float4 *>(cl + W.o_brec),
                       reinterpret_cast<const unsigned short *>(cl + W.o_jp), reinterpret_cast<uint4 *>(const_cast<unsigned char *>(cl) + W.o_pub), my_evals);
         PCL_WTICK(2)
         // statistics: evaluations executed for cloud c (before the task counts as done: the owner reads the total at the end)

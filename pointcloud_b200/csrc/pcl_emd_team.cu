@@ -31,7 +31,7 @@ emd_team_kernel(Pts xyz1, Pts xyz2, int B, int N, float eps, int iters, int flag
     extern __shared__ __align__(16) unsigned char smem_raw[];
     const int tid = threadIdx.x, T = EMD_THREADS, lane = tid & 31, wid = tid >> 5;
     const EmdSmem S = carve(smem_raw, nullptr, N, flags, pcap);
-    if ((int)blockIdx.x >= B) { team_worker(S, W, B, N, eps, (int)blockIdx.x - B, 0, prof ? prof + (size_t)blockIdx.x * 16 : nullptr); return; }
+    if ((int)blockIdx.x >= B) { team_worker<EMD_THREADS>(S, W, B, N, eps, (int)blockIdx.x - B, 0, prof ? prof + (size_t)blockIdx.x * 16 : nullptr); return; }
     // development aid (PCL_EMD_PROFILE): clock totals of thread 0 per phase -> prof[blockIdx.x * 16 + phase]
     long long pt[12] = {0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0}, pc = prof ? clock64() : 0;
 #define PCL_TICK(i) if (prof) { const long long now_ = clock64(); pt[i] += now_ - pc; pc = now_; }
@@ -47,7 +47,7 @@ emd_team_kernel(Pts xyz1, Pts xyz2, int B, int N, float eps, int iters, int flag
     unsigned short *const g_jp = reinterpret_cast<unsigned short *>(cl + W.o_jp);
     uint4 *const g_pub = reinterpret_cast<uint4 *>(cl + W.o_pub);
 
-    emd_setup(S, xyz1, xyz2, cloud, N, flags);
+    emd_setup<EMD_THREADS>(S, xyz1, xyz2, cloud, N, flags);
     __syncthreads();
     // the mirror of the hot state: targets (c = 3: price 0), prices, original target indices, tile boxes
     copy16_out(g_tgt, S.tgt, n32);
@@ -217,7 +217,7 @@ emd_team_kernel(Pts xyz1, Pts xyz2, int B, int N, float eps, int iters, int flag
                 __syncthreads();
                 const int task = S.wsum[56];
                 if (task < 0) break;
-                team_run_task(S, NT, eps, h, task, g_brec, g_jp, g_pub, my_evals);
+                team_run_task<EMD_THREADS>(S, NT, eps, h, task, g_brec, g_jp, g_pub, my_evals);
                 __threadfence();
                 __syncthreads();
                 if (tid == 0) { __threadfence(); atomicAdd(&ctl->done, 1u); }
@@ -281,8 +281,10 @@ emd_team_kernel(Pts xyz1, Pts xyz2, int B, int N, float eps, int iters, int flag
             S.pf[o] = pnew;
             S.tgt[o].w = cnew;
             if (team) { g_pf[o] = pnew; g_tgt[o].w = cnew; }  // U never grows: once the owner works alone the mirror is not read again
-            S.maxinc[o] = -1e9f;
-            S.maxidx[o] = -1;
+            if (!last) {  // (in the last iteration every bidder commits: resetting here would hide the winner from the statistics of a later thread)
+                S.maxinc[o] = -1e9f;
+                S.maxidx[o] = -1;
+            }
         }
         have_list = (U <= 32);
         if (have_list && wid == 0) {
@@ -380,7 +382,7 @@ __global__ void __launch_bounds__(EMD_THREADS, 1)
 emd_worker_kernel(TeamWs W, int B, int N, float eps, int flags, int pcap, long long idle_limit, long long *__restrict__ prof) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     const EmdSmem S = carve(smem_raw, nullptr, N, flags, pcap);
-    team_worker(S, W, B, N, eps, (int)blockIdx.x, idle_limit, prof ? prof + (size_t)blockIdx.x * 16 : nullptr);
+    team_worker<EMD_THREADS>(S, W, B, N, eps, (int)blockIdx.x, idle_limit, prof ? prof + (size_t)blockIdx.x * 16 : nullptr);
 }
 
 }  // namespace
