@@ -9,13 +9,13 @@ from . import cfg
 from .chamfer import chamfer_distance, chamfer_forward_raw
 from .emd_module import emdFunction, emdModule, emd_forward_raw, set_emd_path
 from .losses import (ChamferDistance, EarthMoverDistance, FilterClasses, FilteringChamferDistance,
-                     SegmentingChamferDistance)
+                     SegmentingChamferDistance, chamfer_emd_loss)
 from .sampling import farthest_point_sample, query_ball_point, sample_farthest_points
 from .sharded import ShardedChamferEmdStep, ShardedLoss, shard_bounds
 
 __all__ = [
     "cfg", "chamfer_distance", "chamfer_forward_raw", "emdFunction", "emdModule", "emd_forward_raw", "set_emd_path",
     "ChamferDistance", "FilteringChamferDistance", "SegmentingChamferDistance", "EarthMoverDistance",
-    "FilterClasses", "ShardedLoss", "ShardedChamferEmdStep", "shard_bounds",
+    "FilterClasses", "chamfer_emd_loss", "ShardedLoss", "ShardedChamferEmdStep", "shard_bounds",
     "farthest_point_sample", "sample_farthest_points", "query_ball_point",
 ]

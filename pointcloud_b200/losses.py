@@ -372,3 +372,56 @@ class EarthMoverDistance:
         self.log('train_loss/EMD', point_l)
         self.log('train_loss/feature', feature_l)
         return point_l + feature_l
+
+
+class _ChamferEmdStep(torch.autograd.Function):
+    """Chamfer loss and unweighted EMD loss of one batch in ONE C-ABI call (`pcl_chamfer_emd_step`, include/pcl.h): the auction with
+    its fused epilogue on the caller's stream, Chamfer forward + backward next to it on the library's side stream.  Both gradients are
+    produced by the forward call (as the reference's training step needs them anyway); backward only scales and adds them."""
+
+    @staticmethod
+    def forward(ctx, pred, target, eps, iters, chamfer_mode):
+        _lib.require_cuda()
+        L = _lib.lib()
+        p, t = _lib.as_points(pred), _lib.as_points(target)
+        b, n, _ = p.shape
+        assert t.shape[0] == b and t.shape[1] == n and p.shape[2] >= 3 and t.shape[2] >= 3
+        dev = p.device
+        with _lib.on_device(dev):
+            out = torch.empty(8, device=dev, dtype=torch.float32)
+            g_ch = torch.empty(b, n, 3, device=dev, dtype=torch.float32)
+            g_emd = torch.empty(b, n, 3, device=dev, dtype=torch.float32)
+            nbytes = _STEP_BYTES.get((b, n))
+            if nbytes is None:
+                nbytes = _STEP_BYTES[(b, n)] = L.pcl_chamfer_emd_step_scratch_bytes(b, n)
+            scratch = torch.empty(nbytes, device=dev, dtype=torch.uint8)
+            rc = L.pcl_chamfer_emd_step(*_lib.pts_args(p), *_lib.pts_args(t), b, n, float(eps), int(iters), int(chamfer_mode), out.data_ptr(),
+                                        g_ch.data_ptr(), g_emd.data_ptr(), scratch.data_ptr(), nbytes, _lib.stream_ptr(dev))
+            _lib.check(rc, "pcl_chamfer_emd_step")
+        ctx.save_for_backward(g_ch, g_emd)
+        ctx.meta = (pred.shape, pred.dtype)
+        return out[0] + out[1], out[6]
+
+    @staticmethod
+    def backward(ctx, g_chamfer, g_emd_loss):
+        g_ch, g_emd = ctx.saved_tensors
+        shape, dtype = ctx.meta
+        g = g_ch * g_chamfer + g_emd * g_emd_loss
+        if shape[2] != 3:  # more channels than xyz: only xyz receives gradient
+            full = torch.zeros(shape, device=g.device, dtype=torch.float32)
+            full[:, :, :3] = g
+            g = full
+        return g.to(dtype), None, None, None, None
+
+
+_STEP_BYTES = {}
+
+
+def chamfer_emd_loss(pred, target, eps=0.005, iters=50, chamfer_mode=None):
+    """(chamfer_loss, emd_loss) of a batch -- pytorch3d-style Chamfer (point mean, batch mean, both directions summed; utils.py:211) and
+    mean sqrt of the auction distance (utils.py:304 with weights == 1) -- from ONE fused call.  Differentiable w.r.t. `pred` (B,N,>=3);
+    `target` (B,N,>=3) gets no gradient.  Equivalent to chamfer_distance(pred, target)[0] and emdModule()(pred, target, eps, iters)[0]
+    .sqrt().mean(), but the two losses run concurrently and their backward is a scale-and-add."""
+    if chamfer_mode is None:
+        chamfer_mode = 1 if cfg.chamfer_mode == "fma" else 0
+    return _ChamferEmdStep.apply(pred, target, eps, iters, chamfer_mode)

@@ -301,3 +301,23 @@ def test_class_filter_kernel_matches_the_reference_loop():
     l1 = FilteringChamferDistance(FilterClasses([1], label_dim=3))(pred, tc)
     l2 = FilteringChamferDistance(lambda p: FilterClasses([1], label_dim=3)(p))(pred, tc)
     assert float(l1) == pytest.approx(float(l2), rel=REL)
+
+
+def test_chamfer_emd_loss_equals_the_separate_calls():
+    """pcl.chamfer_emd_loss (one fused C-ABI call, both gradients from the forward) == chamfer_distance + emdModule().sqrt().mean()
+    with autograd, value and gradient, including extra channels and upstream gradients other than 1."""
+    x1, t = synth.table_clouds(6, 1024, seed=77, regime="noisy")
+    pred6 = torch.cat([x1, torch.rand(6, 1024, 3)], dim=2).cuda()
+    target = t.cuda()
+    for p0, tg in ((x1.cuda(), target[:, :, :3].contiguous()), (pred6, target)):
+        pa = p0.clone().requires_grad_()
+        c, e = pcl.chamfer_emd_loss(pa, tg, 0.005, 50)
+        (2.0 * c + 0.5 * e).backward()
+        pb = p0.clone().requires_grad_()
+        c2, _ = pcl.chamfer_distance(pb[:, :, :3], tg[:, :, :3])
+        d, _ = pcl.emdModule()(pb[:, :, :3], tg[:, :, :3], 0.005, 50)
+        e2 = d.sqrt().mean()
+        (2.0 * c2 + 0.5 * e2).backward()
+        assert abs(float(c) - float(c2)) <= 1e-6 * abs(float(c2)) and abs(float(e) - float(e2)) <= 1e-6 * abs(float(e2))
+        assert pa.grad.shape == pb.grad.shape
+        assert torch.allclose(pa.grad, pb.grad, rtol=1e-5, atol=1e-9)

@@ -47,13 +47,13 @@ int main(int argc, char **argv) {
     const float eps = 0.005f;
     const int Gs[4] = {32, 8, 4, 1};
     /* totals[scheme][thr][g] */
-    double tot[2][2][4] = {{{0}}}, alg = 0, exact_needed = 0;
+    double tot[2][2][4] = {{{0}}}, alg = 0, exact_needed = 0, exact_home = 0, home_tiles = 0;
     for (int c = 0; c < B; c++) {
         float *x1 = malloc(12 * n), *x2 = malloc(12 * n);
         msort(raw + ((size_t)c * 2) * n * 3, n, x1);
         msort(raw + ((size_t)c * 2 + 1) * n * 3, n, x2);
         int *asg = malloc(4 * n), *inv = malloc(4 * n), *bid = malloc(4 * n), *maxidx = malloc(4 * n), *un = malloc(4 * n);
-        float *price = calloc(n, 4), *inc = malloc(4 * n), *maxinc = calloc(n, 4), *T2 = malloc(4 * n), *tms = malloc(4 * n);
+        float *price = calloc(n, 4), *inc = malloc(4 * n), *maxinc = calloc(n, 4), *T2 = malloc(4 * n), *tms = malloc(4 * n), *tmh = malloc(4 * n);
         int(*seed)[4] = malloc(16 * n);
         for (int j = 0; j < n; j++) { asg[j] = inv[j] = -1; for (int s = 0; s < 4; s++) seed[j][s] = -1; }
         Box *bx = malloc(sizeof(Box) * NT), *ba = malloc(sizeof(Box) * NT), *bf = malloc(sizeof(Box) * NT);
@@ -107,6 +107,19 @@ int main(int argc, char **argv) {
                 float hi = -1e9f, lo = -1e9f;
                 for (int s = 0; s < ns; s++) { if (sv[s] > hi) { lo = hi; hi = sv[s]; } else if (sv[s] > lo) lo = sv[s]; }
                 tms[j] = lo - 2e-6f;
+                {   /* threshold after a pre-pass over the tile of the previous best object (or of the own Morton rank) */
+                    float h1 = hi, h2 = lo;
+                    const int ht = (seed[j][0] >= 0 ? seed[j][0] : j) / TILE;
+                    for (int k = ht * TILE; k < n && k < (ht + 1) * TILE; k++) {
+                        int dup = 0;
+                        for (int s2 = 0; s2 < 4; s2++) dup |= seed[j][s2] == k;
+                        if (dup) continue;
+                        const float dx = x2[3 * k] - a[0], dy = x2[3 * k + 1] - a[1], dz = x2[3 * k + 2] - a[2];
+                        const float v = 3.f - sqrtf(dx * dx + dy * dy + dz * dz) - price[k];
+                        if (v > h1) { h2 = h1; h1 = v; } else if (v > h2) h2 = v;
+                    }
+                    tmh[j] = h2 - 2e-6f;
+                }
                 float v4[4] = {-1e9f, -1e9f, -1e9f, -1e9f}; int k4[4] = {-1, -1, -1, -1};
                 for (int k = 0; k < n; k++) {
                     const float dx = x2[3 * k] - a[0], dy = x2[3 * k + 1] - a[1], dz = x2[3 * k + 2] - a[2];
@@ -115,6 +128,7 @@ int main(int argc, char **argv) {
                     while (p > 0 && v > v4[p - 1]) p--;
                     if (p < 4) { for (int s = 3; s > p; s--) { v4[s] = v4[s - 1]; k4[s] = k4[s - 1]; } v4[p] = v; k4[p] = k; }
                     if (v >= tms[j]) exact_needed += 1;
+                    if (v >= tmh[j]) exact_home += 1;
                 }
                 bid[j] = k4[0]; inc[j] = v4[0] - v4[1] + eps; T2[j] = v4[1] - 2e-6f;
                 for (int s = 0; s < 4; s++) seed[j][s] = k4[s];
@@ -146,6 +160,14 @@ int main(int argc, char **argv) {
                     }
                 }
             }
+            for (int q0 = 0; q0 < u; q0 += 32) {
+                const int q1 = q0 + 32 < u ? q0 + 32 : u;
+                for (int tl = 0; tl < NT; tl++) {
+                    int s0 = 1;
+                    for (int q = q0; q < q1 && s0; q++) if (!skippable(&bx[tl], x1 + 3 * un[q], tmh[un[q]])) s0 = 0;
+                    if (!s0) home_tiles += (double)(q1 - q0) * TILE;
+                }
+            }
             for (int s = 0; s < 2; s++) for (int thr = 0; thr < 2; thr++) for (int gi = 0; gi < 4; gi++) tot[s][thr][gi] += it_cnt[s][thr][gi];
             if (verbose && c == 0) {
                 float pm = 0; for (int k = 0; k < n; k++) pm = fmaxf(pm, price[k]);
@@ -169,6 +191,7 @@ int main(int argc, char **argv) {
         }
     }
     printf("algorithmic pairs %.4g; candidates above the seed threshold (exact evaluations needed) %.4g = %.4f\n", alg, exact_needed, exact_needed / alg);
+    printf("with a pre-pass over the tile of the previous best object: candidates above the threshold %.4f of the pairs, executed/algorithmic (G=32) %.4f\n", exact_home / alg, home_tiles / alg);
     for (int s = 0; s < 2; s++)
         for (int thr = 0; thr < 2; thr++) {
             printf("scheme %d (%s) threshold %-5s: executed/algorithmic for G=32,8,4,1:", s, s ? "free objects in own tiles" : "shipped", thr ? "final" : "seed");
