@@ -321,3 +321,32 @@ def test_chamfer_emd_loss_equals_the_separate_calls():
         assert abs(float(c) - float(c2)) <= 1e-6 * abs(float(c2)) and abs(float(e) - float(e2)) <= 1e-6 * abs(float(e2))
         assert pa.grad.shape == pb.grad.shape
         assert torch.allclose(pa.grad, pb.grad, rtol=1e-5, atol=1e-9)
+
+
+def test_ticket_path_is_capturable_in_a_cuda_graph():
+    """The ticket path launches its worker kernel on a library-owned stream (forked / joined with events): the pair must record into a CUDA
+    graph like the composite step does, and replaying the graph on new inputs must give the oracle's assignment."""
+    import oracle
+    b, n = 48, 2048                       # clusters of 2 + 52 worker CTAs
+    xa, ta = synth.table_clouds(b, n, seed=5, regime="independent")
+    xb, tb = synth.table_clouds(b, n, seed=6, regime="noisy")
+    x1, x2 = xa.cuda(), ta[:, :, :3].contiguous().cuda()
+    pcl.set_emd_path("tickets")
+    try:
+        side = torch.cuda.Stream()
+        side.wait_stream(torch.cuda.current_stream())
+        with torch.cuda.stream(side):
+            pcl.emd_forward_raw(x1, x2, 0.005, 50)   # warm-up outside the capture (attributes, streams, events exist)
+        torch.cuda.current_stream().wait_stream(side)
+        torch.cuda.synchronize()
+        g = torch.cuda.CUDAGraph()
+        with torch.cuda.graph(g):
+            d, a, _ = pcl.emd_forward_raw(x1, x2, 0.005, 50)
+        for xs, ts in ((xb, tb), (xa, ta)):
+            x1.copy_(xs.cuda()); x2.copy_(ts[:, :, :3].contiguous().cuda())
+            g.replay()
+            torch.cuda.synchronize()
+            o = oracle.emd_forward(xs, ts[:, :, :3].contiguous(), 0.005, 50, nthreads=16)
+            assert np.array_equal(npy(a), o["assignment"]) and np.array_equal(npy(d), o["dist"])
+    finally:
+        pcl.set_emd_path("auto")
