@@ -72,6 +72,13 @@ PCL_API int pcl_device_info(int *sm_count, int *cc_major, int *cc_minor, int *ma
  *   loss_xy[4] = { sum_n mean_i dist_x / max(B,1), same for y,  sum_n mean_i dist_x, same for y }
  *   (loss = loss_xy[0]+loss_xy[1]; [2..3] are the un-normalised batch sums a batch-sharded caller all-reduces)
  */
+/*
+ * D == 3 has two forward implementations with identical results: a brute-force scan of all P1*P2 pairs, and -- for clouds of at
+ * least `min_points` (default 6144) and at most 16384 points -- a spatially pruned one (both clouds in Morton order, 32-point tiles
+ * with bounding boxes, only the tiles that can hold a nearer point are scanned).  pcl_chamfer_set_prune_min moves the switch-over
+ * (0: never prune, < 0: default); a tuning knob, process-wide.
+ */
+PCL_API int pcl_chamfer_set_prune_min(int min_points);
 PCL_API size_t pcl_chamfer_workspace_bytes(int B, int P1, int P2);
 PCL_API int pcl_chamfer_fwd(const void *x, int x_dtype, int64_t x_bs, int64_t x_rs, const int64_t *x_len,
                     const void *y, int y_dtype, int64_t y_bs, int64_t y_rs, const int64_t *y_len,

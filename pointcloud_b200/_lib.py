@@ -24,6 +24,7 @@ _SIGNATURES = {
     "pcl_version": (c_int, []),
     "pcl_last_error": (ctypes.c_char_p, []),
     "pcl_device_info": (c_int, [ctypes.POINTER(c_int)] * 4),
+    "pcl_chamfer_set_prune_min": (c_int, [c_int]),
     "pcl_chamfer_workspace_bytes": (c_size_t, [c_int, c_int, c_int]),
     "pcl_chamfer_fwd": (c_int, _PTS + [c_void_p] + _PTS + [c_void_p] + [c_int] * 5 + [c_void_p] * 5 + [c_void_p, c_size_t, c_void_p]),
     "pcl_chamfer_bwd": (c_int, _PTS + [c_void_p] + _PTS + [c_void_p] + [c_int] * 4 + [c_void_p] * 5 + [c_void_p]),

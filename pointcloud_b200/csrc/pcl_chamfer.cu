@@ -344,6 +344,255 @@ chamfer_nn3_kernel(Pts x, const int64_t *__restrict__ x_len, Pts y, const int64_
     finish_block(s, partial, nblk, dir, n, ticket, P1, P2, x_len, y_len, loss_xy);
 }
 
+
+// ---- spatially pruned nearest neighbour for D == 3 (large clouds) ------------------------------------------------------------------
+// The brute-force scan above is O(P1 * P2).  Here both clouds are first put into Morton order (cells of a 32^3 grid over their common
+// bounding box; counting sort in shared memory; cell mates ranked by original index, so the order is a deterministic function of the
+// input) and cut into tiles of 32 points with bounding boxes; then a warp of 32 neighbouring queries visits only the tiles whose box can
+// still hold a nearer point: 32 tiles are box-tested per ballot against the warp's query box and its largest running minimum, survivors
+// get the per-query test, and what is left is scanned with the ORACLE's arithmetic and the explicit rule "smaller distance, then lower
+// original index".  A tile is skipped only when its box distance (shrunk by 2^-20 relative against rounding) is STRICTLY larger than the
+// running minimum of every query, so distances, indices and the lowest-index tie rule are exactly the brute-force ones; non-finite
+// coordinates switch the pruning off for the tiles / queries they touch (slower, still exact).
+constexpr int PR_THREADS = 512;                 // sort kernel
+constexpr int PR_CELL_BITS = 15;                // 32^3 Morton cells
+constexpr int PR_CELLS = 1 << PR_CELL_BITS;
+constexpr int PR_MAX_P = 16384;                 // shared memory of the sort: 128 KB histogram + 4 B per point
+constexpr int PR_NN_WARPS = 4;                  // nearest-neighbour kernel: 4 warps x 32 queries per CTA
+
+struct PruneWs {                                // workspace regions, per direction d (0: cloud x, 1: cloud y)
+    float4 *pts[2];                             // B x Ppad sorted points {x, y, z, original index bits}, Ppad = P rounded up to 32
+    float4 *box[2];                             // B x NT x 2: {min xyz, flag (1: some point of the tile is not finite)}, {max xyz, -}
+    int ppad[2], nt[2];
+};
+
+__device__ __forceinline__ unsigned spread5(unsigned v) {  // 5 bits -> every third bit
+    v = (v | (v << 8)) & 0x0000100Fu;
+    v = (v | (v << 4)) & 0x000010C3u;
+    v = (v | (v << 2)) & 0x00001249u;
+    return v;
+}
+__device__ __forceinline__ bool finite3(float3 p) { return fabsf(p.x) <= 3.0e38f && fabsf(p.y) <= 3.0e38f && fabsf(p.z) <= 3.0e38f; }
+
+// grid (B, 2): CTA (n, d) sorts the first len points of cloud d of batch element n and zero-fills the outputs of its padded rows.
+__global__ void __launch_bounds__(PR_THREADS, 1)
+chamfer_sort_kernel(Pts x, const int64_t *__restrict__ x_len, Pts y, const int64_t *__restrict__ y_len, int P1, int P2, PruneWs W,
+                    float *__restrict__ dist_x, int *__restrict__ idx_x, float *__restrict__ dist_y, int *__restrict__ idx_y) {
+    extern __shared__ __align__(16) unsigned char pr_smem[];
+    int *hist = reinterpret_cast<int *>(pr_smem);                 // PR_CELLS cell counts, then offsets | arrivals << 16
+    unsigned *tmp = reinterpret_cast<unsigned *>(hist + PR_CELLS + 32);  // P (cell-ordered original indices)
+    __shared__ float red[6][PR_THREADS / 32];
+    __shared__ float bb[6];
+    const int n = blockIdx.x, d = blockIdx.y, tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
+    const Pts me = d ? y : x, other = d ? x : y;
+    const int P = d ? P2 : P1;
+    const int len = d ? len_of(y_len, n, P2) : len_of(x_len, n, P1), olen = d ? len_of(x_len, n, P1) : len_of(y_len, n, P2);
+    float *dist = (d ? dist_y : dist_x) + (size_t)n * P;
+    int *idx = (d ? idx_y : idx_x) + (size_t)n * P;
+    for (int i = len + tid; i < P; i += PR_THREADS) { dist[i] = 0.f; idx[i] = 0; }  // padded rows (knn leaves them at 0)
+    // common bounding box of both clouds (finite coordinates only): the two directions use the same grid
+    float lo[3] = {3e38f, 3e38f, 3e38f}, hi[3] = {-3e38f, -3e38f, -3e38f};
+    for (int pass = 0; pass < 2; pass++) {
+        const Pts &c = pass ? other : me;
+        const int l = pass ? olen : len;
+        for (int i = tid; i < l; i += PR_THREADS) {
+            const float3 p = ld_xyz(c, n, i);
+            if (finite3(p)) {
+                lo[0] = fminf(lo[0], p.x); lo[1] = fminf(lo[1], p.y); lo[2] = fminf(lo[2], p.z);
+                hi[0] = fmaxf(hi[0], p.x); hi[1] = fmaxf(hi[1], p.y); hi[2] = fmaxf(hi[2], p.z);
+            }
+        }
+    }
+#pragma unroll
+    for (int k = 0; k < 3; k++) {
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) { lo[k] = fminf(lo[k], __shfl_xor_sync(0xffffffffu, lo[k], o)); hi[k] = fmaxf(hi[k], __shfl_xor_sync(0xffffffffu, hi[k], o)); }
+        if (lane == 0) { red[k][wid] = lo[k]; red[3 + k][wid] = hi[k]; }
+    }
+    for (int c = tid; c < PR_CELLS + 32; c += PR_THREADS) hist[c] = 0;
+    __syncthreads();
+    if (tid < 6) {
+        float v = red[tid][0];
+        for (int w = 1; w < PR_THREADS / 32; w++) v = tid < 3 ? fminf(v, red[tid][w]) : fmaxf(v, red[tid][w]);
+        bb[tid] = v;
+    }
+    __syncthreads();
+    float sc[3];
+#pragma unroll
+    for (int k = 0; k < 3; k++) sc[k] = (bb[3 + k] > bb[k]) ? 32.f / (bb[3 + k] - bb[k]) : 0.f;
+    auto cell_of = [&](float3 p) -> int {
+        if (!finite3(p)) return PR_CELLS - 1;
+        const unsigned qx = (unsigned)min(max((int)((p.x - bb[0]) * sc[0]), 0), 31), qy = (unsigned)min(max((int)((p.y - bb[1]) * sc[1]), 0), 31),
+                       qz = (unsigned)min(max((int)((p.z - bb[2]) * sc[2]), 0), 31);
+        return (int)(spread5(qx) | (spread5(qy) << 1) | (spread5(qz) << 2));
+    };
+    for (int i = tid; i < len; i += PR_THREADS) atomicAdd(&hist[cell_of(ld_xyz(me, n, i))], 1);
+    __syncthreads();
+    {   // exclusive prefix sum over the cells: 64 consecutive cells per thread + block scan
+        constexpr int CPT = PR_CELLS / PR_THREADS;
+        int sum = 0;
+        for (int i = 0; i < CPT; i++) sum += hist[tid * CPT + i];
+        int incl = sum;
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) { const int u = __shfl_up_sync(0xffffffffu, incl, o); if (lane >= o) incl += u; }
+        __shared__ int wsum[PR_THREADS / 32];
+        if (lane == 31) wsum[wid] = incl;
+        __syncthreads();
+        int base = incl - sum;
+        for (int w = 0; w < wid; w++) base += wsum[w];
+        for (int i = 0; i < CPT; i++) { const int v = hist[tid * CPT + i]; hist[tid * CPT + i] = base; base += v; }
+    }
+    __syncthreads();
+    // Cell mates in arrival order (tmp), then every point takes the rank of its original index among them: a deterministic order
+    // (the per-CTA partial sums of the loss depend on it).  The arrival counter of a cell lives in the upper half of its offset word
+    // (offsets and counts are <= 16384 = PR_MAX_P).
+    for (int i = tid; i < len; i += PR_THREADS) {
+        const int c = cell_of(ld_xyz(me, n, i));
+        const unsigned old = (unsigned)atomicAdd(&hist[c], 0x10000);
+        tmp[(old & 0xffffu) + (old >> 16)] = (unsigned)i;
+    }
+    __syncthreads();
+    float4 *out = W.pts[d] + (size_t)n * W.ppad[d];
+    for (int i = tid; i < len; i += PR_THREADS) {
+        const float3 p = ld_xyz(me, n, i);
+        const unsigned h = (unsigned)hist[cell_of(p)];
+        const int s0 = (int)(h & 0xffffu), s1 = s0 + (int)(h >> 16);
+        int pos = s0;
+        for (int q = s0; q < s1; q++) pos += (tmp[q] < (unsigned)i) ? 1 : 0;
+        out[pos] = make_float4(p.x, p.y, p.z, __int_as_float(i));
+    }
+    const int NT = W.nt[d];
+    for (int i = len + tid; i < NT * 32 && i < W.ppad[d]; i += PR_THREADS) out[i] = make_float4(0.f, 0.f, 0.f, __int_as_float(0x7fffffff));  // tail of the last tile (never read as a point: j < cnt)
+    __threadfence_block();
+    __syncthreads();
+    float4 *box = W.box[d] + (size_t)n * NT * 2;
+    for (int t = wid; t * 32 < len; t += PR_THREADS / 32) {
+        const int i = t * 32 + lane;
+        const bool ok = i < len;
+        const float4 p = ok ? out[i] : make_float4(0.f, 0.f, 0.f, 0.f);
+        const bool fin = !ok || finite3(make_float3(p.x, p.y, p.z));
+        float l0 = (ok && fin) ? p.x : 3e38f, l1 = (ok && fin) ? p.y : 3e38f, l2 = (ok && fin) ? p.z : 3e38f;
+        float h0 = (ok && fin) ? p.x : -3e38f, h1 = (ok && fin) ? p.y : -3e38f, h2 = (ok && fin) ? p.z : -3e38f;
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) {
+            l0 = fminf(l0, __shfl_xor_sync(0xffffffffu, l0, o)); l1 = fminf(l1, __shfl_xor_sync(0xffffffffu, l1, o)); l2 = fminf(l2, __shfl_xor_sync(0xffffffffu, l2, o));
+            h0 = fmaxf(h0, __shfl_xor_sync(0xffffffffu, h0, o)); h1 = fmaxf(h1, __shfl_xor_sync(0xffffffffu, h1, o)); h2 = fmaxf(h2, __shfl_xor_sync(0xffffffffu, h2, o));
+        }
+        const bool anybad = __any_sync(0xffffffffu, !fin);
+        if (lane == 0) { box[2 * t] = make_float4(l0, l1, l2, anybad ? 1.f : 0.f); box[2 * t + 1] = make_float4(h0, h1, h2, 0.f); }
+    }
+}
+
+// squared distance between two boxes / a point and a box (0 inside); NaN-free for finite boxes
+__device__ __forceinline__ float box_gap2(float alo, float ahi, float blo, float bhi) {
+    const float g = fmaxf(fmaxf(blo - ahi, alo - bhi), 0.f);
+    return g * g;
+}
+
+// grid (ceil(maxP / 128), B, 2): warp = 32 consecutive queries of the SORTED query cloud.
+template <bool FMA>
+__global__ void __launch_bounds__(PR_NN_WARPS * 32)
+chamfer_nn3_pruned_kernel(const int64_t *__restrict__ x_len, const int64_t *__restrict__ y_len, int P1, int P2, PruneWs W,
+                          float *__restrict__ dist_x, int *__restrict__ idx_x, float *__restrict__ dist_y, int *__restrict__ idx_y,
+                          float *__restrict__ partial, int nblk, unsigned *__restrict__ ticket, float *__restrict__ loss_xy) {
+    __shared__ float red[PR_NN_WARPS];
+    const int dir = blockIdx.z, n = blockIdx.y, lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+    const int PQ = dir ? P2 : P1;
+    const int q0 = (blockIdx.x * PR_NN_WARPS + wid) * 32;
+    const int lq = dir ? len_of(y_len, n, P2) : len_of(x_len, n, P1);
+    const int lt = dir ? len_of(x_len, n, P1) : len_of(y_len, n, P2);
+    const int dq = dir, dt = dir ^ 1;
+    const float INF = __int_as_float(0x7f800000);
+    float s = 0.f;
+    if (q0 < lq) {  // warp-uniform
+        const float4 *qp = W.pts[dq] + (size_t)n * W.ppad[dq];
+        const float4 *tp = W.pts[dt] + (size_t)n * W.ppad[dt];
+        const float4 *tb = W.box[dt] + (size_t)n * W.nt[dt] * 2;
+        const bool valid = q0 + lane < lq;
+        const float4 q = valid ? qp[q0 + lane] : qp[q0];           // surplus lanes shadow the first query (results discarded)
+        const int qi = __float_as_int(q.w);
+        float best = INF;
+        int bi = 0x7fffffff;
+        if (lt > 0) {
+            const int NTt = (lt + 31) >> 5;
+            // the warp's query box; a non-finite query makes it infinite (nothing is pruned by the bulk test)
+            const bool qfin = finite3(make_float3(q.x, q.y, q.z));
+            float bl0 = q.x, bl1 = q.y, bl2 = q.z, bh0 = q.x, bh1 = q.y, bh2 = q.z;
+#pragma unroll
+            for (int o = 16; o > 0; o >>= 1) {
+                bl0 = fminf(bl0, __shfl_xor_sync(0xffffffffu, bl0, o)); bl1 = fminf(bl1, __shfl_xor_sync(0xffffffffu, bl1, o)); bl2 = fminf(bl2, __shfl_xor_sync(0xffffffffu, bl2, o));
+                bh0 = fmaxf(bh0, __shfl_xor_sync(0xffffffffu, bh0, o)); bh1 = fmaxf(bh1, __shfl_xor_sync(0xffffffffu, bh1, o)); bh2 = fmaxf(bh2, __shfl_xor_sync(0xffffffffu, bh2, o));
+            }
+            const bool allfin = __all_sync(0xffffffffu, qfin);
+            auto scan = [&](int tl) {
+                const int cnt = min(32, lt - tl * 32);
+                const float4 *tt = tp + (size_t)tl * 32;
+#pragma unroll 4
+                for (int j = 0; j < cnt; j++) {
+                    const float4 t = __ldg(tt + j);
+                    const float dd = sqdist3<FMA>(q.x, q.y, q.z, t);
+                    const int ti = __float_as_int(t.w);
+                    if (dd < best || (dd == best && ti < bi)) { best = dd; bi = ti; }
+                }
+            };
+            auto lane_skips = [&](const float4 &lo, const float4 &hi) -> bool {  // this query cannot find anything nearer (or equal) in the tile
+                const float d2 = box_gap2(q.x, q.x, lo.x, hi.x) + box_gap2(q.y, q.y, lo.y, hi.y) + box_gap2(q.z, q.z, lo.z, hi.z);
+                return lo.w == 0.f && (d2 * 0.999999f > best);
+            };
+            // Seed: the tile whose box is nearest to the warp's query box (32 boxes per round, warp arg-min) gives every query a tight
+            // running minimum before the candidates are collected; the guess by rank (both clouds are sorted along the same curve) is
+            // the fall-back when no finite box distance exists.
+            int tg = min((int)(((long long)q0 * NTt) / max(lq, 1)), NTt - 1);
+            {
+                float dmin = INF;
+                int tmin = -1;
+                for (int tb0 = 0; tb0 < NTt; tb0 += 32) {
+                    const int tl = tb0 + lane;
+                    if (tl < NTt) {
+                        const float4 lo = __ldg(tb + 2 * tl), hi = __ldg(tb + 2 * tl + 1);
+                        const float d2 = box_gap2(bl0, bh0, lo.x, hi.x) + box_gap2(bl1, bh1, lo.y, hi.y) + box_gap2(bl2, bh2, lo.z, hi.z);
+                        if (lo.w == 0.f && d2 < dmin) { dmin = d2; tmin = tl; }
+                    }
+                }
+                const int key = __reduce_min_sync(0xffffffffu, (dmin < INF) ? __float_as_int(dmin) : 0x7f800000);  // d2 >= 0: integer order == float order
+                const unsigned who = __ballot_sync(0xffffffffu, tmin >= 0 && __float_as_int(dmin) == key);
+                if (allfin && who) tg = __shfl_sync(0xffffffffu, tmin, __ffs(who) - 1);
+            }
+            scan(tg);
+            for (int tb0 = 0; tb0 < NTt; tb0 += 32) {
+                const int tl = tb0 + lane;
+                // largest running minimum of the warp (best >= 0 or +inf / NaN-free: integer order == float order)
+                const float bmax = __int_as_float(__reduce_max_sync(0xffffffffu, __float_as_int(best)));
+                bool cand = false;
+                if (tl < NTt && tl != tg) {
+                    const float4 lo = __ldg(tb + 2 * tl), hi = __ldg(tb + 2 * tl + 1);
+                    const float d2 = box_gap2(bl0, bh0, lo.x, hi.x) + box_gap2(bl1, bh1, lo.y, hi.y) + box_gap2(bl2, bh2, lo.z, hi.z);
+                    cand = !(allfin && lo.w == 0.f && d2 * 0.999999f > bmax);
+                }
+                unsigned cm = __ballot_sync(0xffffffffu, cand);
+                while (cm) {
+                    const int t2 = tb0 + __ffs(cm) - 1;
+                    cm &= cm - 1;
+                    const float4 lo = __ldg(tb + 2 * t2), hi = __ldg(tb + 2 * t2 + 1);
+                    if (__all_sync(0xffffffffu, lane_skips(lo, hi))) continue;
+                    scan(t2);
+                }
+            }
+        }
+        if (valid) {
+            const bool ok = lt > 0;
+            const float dres = ok ? best : 0.f;
+            float *dist = (dir ? dist_y : dist_x) + (size_t)n * PQ;
+            int *idx = (dir ? idx_y : idx_x) + (size_t)n * PQ;
+            dist[qi] = dres;
+            idx[qi] = (ok && bi != 0x7fffffff && best < INF) ? bi : 0;
+            s = dres;
+        }
+    }
+    s = block_sum<PR_NN_WARPS>(s, red);
+    finish_block(s, partial, nblk, dir, n, ticket, P1, P2, x_len, y_len, loss_xy);
+}
+
 // Generic feature width (ChamferDistance over all channels, utils.py:209-211).  One query per thread.
 template <bool FMA, int D>
 __global__ void __launch_bounds__(CH_THREADS)
@@ -462,6 +711,37 @@ int check_args(const void *x, int x_dtype, const void *y, int y_dtype, int B, in
     return PCL_OK;
 }
 
+// workspace of the pruned path, behind [ticket][partials]: sorted clouds and tile boxes of both directions
+inline size_t prune_bytes(int B, int P1, int P2) {
+    if (B <= 0 || P1 <= 0 || P2 <= 0 || P1 > PR_MAX_P || P2 > PR_MAX_P) return 0;
+    size_t o = 0;
+    for (int d = 0; d < 2; d++) {
+        const size_t ppad = (size_t)((d ? P2 : P1) + 31) / 32 * 32;
+        o += align_up((size_t)B * ppad * sizeof(float4), 256) + align_up((size_t)B * (ppad / 32) * 2 * sizeof(float4), 256);
+    }
+    return o;
+}
+inline PruneWs prune_ws(unsigned char *base, int B, int P1, int P2) {
+    PruneWs W;
+    size_t o = 0;
+    for (int d = 0; d < 2; d++) {
+        const size_t ppad = (size_t)((d ? P2 : P1) + 31) / 32 * 32;
+        W.ppad[d] = (int)ppad; W.nt[d] = (int)(ppad / 32);
+        W.pts[d] = reinterpret_cast<float4 *>(base + o); o += align_up((size_t)B * ppad * sizeof(float4), 256);
+        W.box[d] = reinterpret_cast<float4 *>(base + o); o += align_up((size_t)B * (ppad / 32) * 2 * sizeof(float4), 256);
+    }
+    return W;
+}
+// smallest min(P1, P2) that takes the pruned path (0: never).  Measured on B200 (profiles/r2_s2_chamfer_pruned.txt): the brute-force
+// kernel evaluates a pair in 2.5 instructions, the pruned scan in ~12 (oracle arithmetic) on the ~30 % / 6 % of the pairs that survive
+// at N = 2048 / 16384 -- the crossover is near 6000 points.  pcl_chamfer_set_prune_min / PCL_CHAMFER_PRUNE_MIN override it.
+int g_prune_min = -1;
+inline int prune_min() {
+    if (g_prune_min >= 0) return g_prune_min;
+    static const int v = [] { const char *e = getenv("PCL_CHAMFER_PRUNE_MIN"); return e ? atoi(e) : 6144; }();
+    return v;
+}
+
 inline int nblk_for(int P1, int P2) {
     const int maxP = P1 > P2 ? P1 : P2;
     constexpr int G = C3_QUERIES < CH_THREADS ? C3_QUERIES : CH_THREADS;  // queries per CTA of the finer-grained kernel
@@ -473,9 +753,14 @@ inline int nblk_for(int P1, int P2) {
 
 using namespace pcl;
 
+extern "C" int pcl_chamfer_set_prune_min(int min_points) {
+    g_prune_min = min_points;  // < 0: back to the default
+    return PCL_OK;
+}
+
 extern "C" size_t pcl_chamfer_workspace_bytes(int B, int P1, int P2) {
     if (B <= 0) return 256;
-    return 256 + align_up((size_t)2 * B * nblk_for(P1, P2) * sizeof(float), 256);  // [ticket][per-CTA partial sums]
+    return 256 + align_up((size_t)2 * B * nblk_for(P1, P2) * sizeof(float), 256) + prune_bytes(B, P1, P2);  // [ticket][per-CTA partial sums][sorted clouds + tile boxes of the pruned path]
 }
 
 extern "C" int pcl_chamfer_fwd(const void *x, int x_dtype, int64_t x_bs, int64_t x_rs, const int64_t *x_len,
@@ -504,6 +789,29 @@ extern "C" int pcl_chamfer_fwd(const void *x, int x_dtype, int64_t x_bs, int64_t
     float *partial = (float *)((unsigned char *)workspace + 256);
     const int nblk = nblk_for(P1, P2);
     PCL_CUDA(cudaMemsetAsync(ticket, 0, sizeof(unsigned), st));  // every CTA writes its partial (zeros beyond the shorter cloud); the last one sums
+    const int pmin = P1 < P2 ? P1 : P2;
+    if (D == 3 && prune_min() > 0 && pmin >= prune_min() && prune_bytes(B, P1, P2) > 0) {
+        // large clouds: Morton order + tile boxes, then a nearest-neighbour scan that only visits the tiles that can matter
+        const PruneWs W = prune_ws((unsigned char *)workspace + 256 + align_up((size_t)2 * B * nblk * sizeof(float), 256), B, P1, P2);
+        const int maxP = P1 > P2 ? P1 : P2;
+        const size_t smem = (size_t)(PR_CELLS + 32) * sizeof(int) + (size_t)maxP * sizeof(unsigned);
+        static thread_local int attr_dev = -1;
+        int dev = 0;
+        PCL_CUDA(cudaGetDevice(&dev));
+        if (attr_dev != dev) {
+            PCL_CUDA(cudaFuncSetAttribute(chamfer_sort_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)((PR_CELLS + 32) * sizeof(int) + PR_MAX_P * sizeof(unsigned))));
+            attr_dev = dev;
+        }
+        chamfer_sort_kernel<<<dim3(B, 2), PR_THREADS, smem, st>>>(xp, x_len, yp, y_len, P1, P2, W, dist_x, (int *)idx_x, dist_y, (int *)idx_y);
+        PCL_CUDA(cudaGetLastError());
+        const dim3 grid((maxP + PR_NN_WARPS * 32 - 1) / (PR_NN_WARPS * 32), B, 2);
+        if (mode == PCL_CHAMFER_FMA)
+            chamfer_nn3_pruned_kernel<true><<<grid, PR_NN_WARPS * 32, 0, st>>>(x_len, y_len, P1, P2, W, dist_x, (int *)idx_x, dist_y, (int *)idx_y, partial, nblk, ticket, loss_xy);
+        else
+            chamfer_nn3_pruned_kernel<false><<<grid, PR_NN_WARPS * 32, 0, st>>>(x_len, y_len, P1, P2, W, dist_x, (int *)idx_x, dist_y, (int *)idx_y, partial, nblk, ticket, loss_xy);
+        PCL_CUDA(cudaGetLastError());
+        return PCL_OK;
+    }
     rc = (mode == PCL_CHAMFER_FMA)
              ? launch_fwd<true>(xp, x_len, yp, y_len, B, P1, P2, D, dist_x, idx_x, dist_y, idx_y, partial, nblk, ticket, loss_xy, st)
              : launch_fwd<false>(xp, x_len, yp, y_len, B, P1, P2, D, dist_x, idx_x, dist_y, idx_y, partial, nblk, ticket, loss_xy, st);

@@ -159,3 +159,61 @@ def test_chamfer_golden_and_argument_checks(golden):
         pcl.chamfer_distance(torch.rand(1, 4, 9).cuda(), torch.rand(1, 4, 9).cuda())   # D > 8
     l0, _ = pcl.chamfer_distance(torch.rand(0, 5, 3).cuda(), torch.rand(0, 7, 3).cuda())
     assert float(l0) == 0.0
+
+
+@pytest.fixture
+def pruned_everywhere():
+    """Forces the spatially pruned nearest-neighbour path (Morton order + tile boxes) for every cloud size, restores the default after."""
+    L = pcl._lib.lib()
+    L.pcl_chamfer_set_prune_min(1)
+    yield
+    L.pcl_chamfer_set_prune_min(-1)
+
+
+def test_pruned_path_is_bit_exact_vs_oracle(pruned_everywhere):
+    """Same cases as the brute-force kernel's tests, through the pruned path: random, Table-shaped, exact ties (duplicates, lattice),
+    ragged lengths incl. empty clouds, far from the origin / tiny / huge scales, all points equal, non-finite coordinates."""
+    g = torch.Generator().manual_seed(101)
+    for b, p1, p2 in [(4, 2048, 2048), (3, 700, 1300), (2, 21, 2048), (1, 1, 1), (5, 1024, 33), (2, 4100, 4099)]:
+        for mode in ("unfused", "fma"):
+            run_case(torch.rand(b, p1, 3, generator=g), torch.rand(b, p2, 3, generator=g), mode=mode)
+    x, t = synth.table_clouds(4, 2048, seed=2)
+    run_case(x, t[:, :, :3].contiguous())
+    y = torch.rand(2, 512, 3, generator=g)
+    o, r = run_case(torch.rand(2, 300, 3, generator=g), torch.cat([y, y], dim=1))
+    assert (npy(r["idx_x"]) < 512).all()                      # duplicated targets: the lowest index wins
+    run_case(torch.randint(0, 8, (2, 600, 3), generator=g).float() / 8, torch.randint(0, 8, (2, 700, 3), generator=g).float() / 8)
+    x, y = torch.rand(2, 700, 3, generator=g), torch.rand(2, 1100, 3, generator=g)
+    for off in (10.0, 1000.0, -3.0e4):
+        run_case(x + off, y + off)
+    run_case(x * 1e-18, y * 1e-18)
+    run_case(x * 1e15, y * 1e15)
+    run_case(torch.full((2, 300, 3), 0.25), torch.full((2, 500, 3), 0.25))      # every point in one cell
+    xl, yl = torch.tensor([700, 0]), torch.tensor([5, 1100])
+    run_case(x, y, xl, yl)
+    xn = x.clone(); xn[0, 3, 1] = float("nan"); xn[1, 10, 0] = float("inf")
+    yn = y.clone(); yn[0, 7, 2] = float("-inf"); yn[1, 0, 0] = float("nan")
+    o, r = oracle.chamfer_forward(x, yn, mode=0), pcl.chamfer_forward_raw(x.cuda(), yn.cuda())
+    assert np.array_equal(npy(r["idx_x"]), o["idx_x"]) and np.array_equal(npy(r["dist_x"]), o["dist_x"])   # non-finite targets are never nearest
+    o, r = oracle.chamfer_forward(xn, y, mode=0), pcl.chamfer_forward_raw(xn.cuda(), y.cuda())
+    assert np.array_equal(npy(r["idx_y"]), o["idx_y"]) and np.array_equal(npy(r["dist_y"]), o["dist_y"])
+    assert np.array_equal(npy(r["idx_x"]), o["idx_x"]) and np.array_equal(npy(r["dist_x"]), o["dist_x"], equal_nan=True)  # non-finite queries
+
+
+def test_pruned_path_equals_brute_force_at_config5_sizes():
+    """BASELINE config 5's large clouds (the sizes that take the pruned path by default): both implementations must return identical
+    distances and indices (the CPU oracle needs minutes there; it is checked at N=8192 on two clouds)."""
+    L = pcl._lib.lib()
+    for n in (8192, 16384):
+        xu, yu = synth.uniform_clouds(4, n, seed=n)
+        xt, tt = synth.table_clouds(4, n, seed=n + 1)
+        for x, y in ((xu, yu), (xt, tt[:, :, :3].contiguous())):
+            L.pcl_chamfer_set_prune_min(0)
+            a = pcl.chamfer_forward_raw(x.cuda(), y.cuda())
+            L.pcl_chamfer_set_prune_min(-1)
+            b = pcl.chamfer_forward_raw(x.cuda(), y.cuda())
+            for k in ("dist_x", "dist_y", "idx_x", "idx_y"):
+                assert torch.equal(a[k], b[k]), (n, k)
+            assert torch.allclose(a["loss_xy"], b["loss_xy"], rtol=1e-5)
+    x, y = synth.uniform_clouds(2, 8192, seed=3)
+    run_case(x, y)
