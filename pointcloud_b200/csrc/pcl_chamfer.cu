@@ -39,7 +39,7 @@ constexpr int C3_CHUNK = 32;     // ... chunks of 32: the granularity of the app
 #define PCL_C3_GROUP 4
 #endif
 #ifndef PCL_C3_MINB
-#define PCL_C3_MINB 4
+#define PCL_C3_MINB 5  // CTAs per SM the register budget is set for: 5 x 128 threads x 96 registers (4 x 128: 6-10 % slower at every size, 6 x 80: spills)
 #endif
 constexpr int C3_GROUP = PCL_C3_GROUP;      // pairs of targets per register buffer of the scan (double-buffered: hides the LDS latency)
 
