@@ -677,6 +677,59 @@ def main():
         "chamfer_loss (ChamferDistance, 1 all-reduce per call)": class_leg(lambda b, n, seed, regime: tuple(x[:, :, :3].contiguous() for x in synth.table_clouds(b, n, seed=seed, regime=regime)), pcl.ChamferDistance()),
         "path": "pointcloud_b200.ShardedLoss(loss class) forward + backward per step, device-resident inputs, python autograd"}
 
+    # ---- BASELINE config 5: Chamfer fwd+bwd, B=64 GLOBAL, N=M in {1k..16k} (strong scaling: 64/N clouds per rank, the ONE all-reduce of
+    #      the two batch sums inside the step); config 1: the reference's CPU-runnable case (B=8, N=2048) on the GPU and on the CPU port ----
+    def config5_leg():
+        Lc, Ac = _lib.lib(), _lib.pts_args
+        bg = 64
+        bl5 = max(1, bg // world)
+        rows = []
+        for n5 in (1024, 2048, 4096, 8192, 16384):
+            xg, yg = synth.uniform_clouds(bg, n5, seed=0)
+            x5, y5 = xg[rank * bl5:(rank + 1) * bl5].to(device), yg[rank * bl5:(rank + 1) * bl5].to(device)
+            e5 = lambda *sh, dt=torch.float32: torch.empty(*sh, device=device, dtype=dt)
+            dx, dy, ix, iy, lxy = e5(bl5, n5), e5(bl5, n5), e5(bl5, n5, dt=torch.int32), e5(bl5, n5, dt=torch.int32), e5(4)
+            gx, gy, ones = e5(bl5, n5, 3), e5(bl5, n5, 3), torch.ones(2, device=device)
+            wsb = Lc.pcl_chamfer_workspace_bytes(bl5, n5, n5)
+            ws5 = torch.empty(wsb, device=device, dtype=torch.uint8)
+
+            def step5(i):
+                rc = Lc.pcl_chamfer_fwd(*Ac(x5), None, *Ac(y5), None, bl5, n5, n5, 3, 0, dx.data_ptr(), ix.data_ptr(), dy.data_ptr(), iy.data_ptr(),
+                                        lxy.data_ptr(), ws5.data_ptr(), wsb, st)
+                if world > 1:
+                    dist.all_reduce(lxy[2:4])
+                rc |= Lc.pcl_chamfer_bwd(*Ac(x5), None, *Ac(y5), None, bl5, n5, n5, 3, ix.data_ptr(), iy.data_ptr(), ones.data_ptr(), gx.data_ptr(),
+                                         gy.data_ptr(), st)
+                if rc:
+                    raise RuntimeError(Lc.pcl_last_error().decode())
+            k5 = 20 if n5 <= 4096 else 8
+            ms5 = timed(step5, k5, 3) / k5
+            rows.append({"N": n5, "clouds_per_gpu": bl5, "step_ms": ms5, "clouds_per_s": bg / (ms5 * 1e-3),
+                         "algorithmic_fp32_frac": FLOP_PER_CHAMFER_EVAL * 2.0 * bl5 * n5 * n5 / (ms5 * 1e-3) / 1e12 / fp32_peak_tflops})
+        return {"B_global": bg, "scaling": "strong", "rows": rows,
+                "note": "N >= 6144 takes the spatially pruned forward (most pairs are never evaluated: the algorithmic fraction can exceed 1)"}
+
+    def config1_leg():
+        import oracle
+        x1c, t1c = synth.table_clouds(8, NPTS, seed=0)
+        y1c = t1c[:, :, :3].contiguous()
+        xd, yd = x1c.to(device), y1c.to(device)
+
+        def gpu(i):
+            xx = xd.detach().requires_grad_()
+            loss, _ = pcl.chamfer_distance(xx, yd)
+            loss.backward()
+        gms = timed(gpu, 20, 3) / 20
+        t0 = time.perf_counter()
+        for _ in range(3):
+            c = oracle.chamfer_forward(x1c, y1c, nthreads=os.cpu_count() or 1)
+            oracle.chamfer_backward(x1c, y1c, c["idx_x"], c["idx_y"], 1.0)
+        cms = (time.perf_counter() - t0) / 3 * 1e3
+        return {"shape": [8, NPTS, NPTS], "gpu_python_api_fwd_bwd_ms": gms, "cpu_oracle_port_fwd_bwd_ms": cms, "cpu_threads": os.cpu_count()}
+
+    config5 = config5_leg()
+    config1 = config1_leg() if (rank == 0 and world == 1) else None
+
     # ---- parity of the timed step against the oracle; the reference's own step on the same GPU; the CPU baseline ----
     reference_gpu, cb, parity_ok, parity = None, None, None, None
     if rank == 0:
@@ -700,7 +753,9 @@ def main():
                 "clocks": clocks, "e2e": e2e, "gpu_launches": KERNELS_PER_STEP * K, "roofline": roofline,
                 "roofline_chamfer": roofline_chamfer, "roofline_bwd": roofline_bwd, "parity_checked": parity_ok, "parity": parity,
                 "sharded_equals_single_gpu": sharded_equals_single, "strong_scaling": strong, "sharded_api": sharded_api,
-                "cpu_baseline": cb, "breakdown_ms": breakdown, "reference_gpu": reference_gpu, "impl": "ours"}
+                "cpu_baseline": cb, "breakdown_ms": breakdown, "reference_gpu": reference_gpu,
+                "other_configs": {"config1_chamfer_B8_N2048": config1, "config3_segmenter_loss": "sharded_api['segmenter_loss = config 3 ...']",
+                                  "config5_chamfer_sweep_B64": config5}, "impl": "ours"}
         print(json.dumps(line))
     if world > 1:
         dist.destroy_process_group()
