@@ -2,8 +2,11 @@
 //
 // Replaces the reference's 7*iters+1 launches (pointcloud_vision/loss/emd/emd_cuda.cu:256-269:
 // clear, calc_unass_cnt, calc_unass_cnt_sum, calc_unass_idx, Bid, GetMax, Assign, CalcDist) with ONE
-// persistent kernel.  A cloud is owned by a thread-block cluster of CS CTAs (CS in {1,2,4,8,16}, chosen so
-// that B*CS fills the 148 SMs).  Every CTA keeps the whole auction state of its cloud in shared memory
+// persistent kernel.  A cloud is owned by a thread-block cluster of CS CTAs (CS in {1,2,4,8,16}: the largest size
+// for which all B clusters are resident at once; 640-thread CTAs for CS <= 4, 512 otherwise).  This file holds the cluster
+// kernel (and its EXPORT variant, whose heavy iterations are shared with worker CTAs) and the host entry points that pick
+// between it and the owner + worker kernel of pcl_emd_team.cu (pcl_emd_set_path).
+// Every CTA keeps the whole auction state of its cloud in shared memory
 // (targets, prices, assignment, inverse assignment) as a REPLICA:
 //   0. set-up: both clouds are put into an internal Morton order (counting sort over up to 16384 cells + in-cell ranking),
 //      targets are cut into tiles of 32 with a bounding box; every tie rule is evaluated on ORIGINAL indices, so the order never changes a result;
