@@ -134,10 +134,11 @@ def test_team_and_ticket_paths_refuse_what_they_cannot_do(emd_path):
 
 # pick_cluster (csrc/pcl_emd.cu): the largest power of two <= 16 such that all b clusters are resident at once (a cluster lives
 # inside one GPC: 8 clusters of 16 or 16 clusters of 8 do not fit a B200 although 128 <= 148 SMs).  Measured on B200:
-CLUSTER_SIZE_ON_B200 = {4: 16, 8: 8, 16: 4, 32: 4, 40: 2, 80: 1}
+# (which of two sizes fits can depend on how the part's GPCs are populated)
+CLUSTER_SIZE_ON_B200 = {4: (16,), 8: (8, 16), 12: (8,), 16: (4, 8), 32: (4,), 40: (2,), 80: (1,)}
 
 
-@pytest.mark.parametrize("b", [4, 8, 16, 32, 40, 80])
+@pytest.mark.parametrize("b", [4, 8, 12, 16, 32, 40, 80])
 @pytest.mark.parametrize("regime", ["independent", "noisy"])
 def test_emd_bit_exact_at_every_cluster_size_on_the_bench_workload(emd_path, b, regime):
     """The launch bench.py times is B=32, N=2048 -> clusters of 4 CTAs; the dealing of the bidders to the CTAs of a
@@ -155,7 +156,7 @@ def test_emd_bit_exact_at_every_cluster_size_on_the_bench_workload(emd_path, b, 
         st = npy(st)
         assert (st[:, 3] == st[0, 3]).all() and b * int(st[0, 3]) <= sm.value, st[:, 3]
         if sm.value == 148:  # every cluster size 16, 8, 4, 2, 1 is exercised on the machine this is built for
-            assert int(st[0, 3]) == CLUSTER_SIZE_ON_B200[b], st[:, 3]
+            assert int(st[0, 3]) in CLUSTER_SIZE_ON_B200[b], st[:, 3]
         assert np.array_equal(npy(a), o["assignment"]) and np.array_equal(npy(d), o["dist"])
         assert np.array_equal(st[:, 0], o["sum_unass"]) and np.array_equal(st[:, 1], o["iters_run"])
 
