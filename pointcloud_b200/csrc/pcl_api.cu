@@ -142,13 +142,17 @@ extern "C" int pcl_chamfer_emd_step(const void *pred, int dtype1, int64_t bs1, i
                            (int32_t *)(d + L.emd_asg), nullptr, 1.0f / ((float)B * (float)N), grad_pred_emd, losses + 4, d + L.emd_ws,
                            pcl_emd_workspace_bytes(B, N), stream);
     if (rc) return rc;
-    // ... then the side stream: Chamfer forward + backward (upstream gradient 1) fill the remaining SMs
+    // ... then the side stream: Chamfer forward + backward (upstream gradient 1) fill the remaining SMs.  The zero fills of the scatter
+    // targets do not depend on the forward: issued first, they are off the critical path of the late-training steps (where Chamfer on the
+    // 20 free SMs, not the auction, ends the step)
+    PCL_CUDA(cudaMemsetAsync(grad_pred_chamfer, 0, (size_t)B * N * 3 * sizeof(float), ss->side));
+    PCL_CUDA(cudaMemsetAsync(d + L.grad_y, 0, (size_t)B * N * 3 * sizeof(float), ss->side));
     rc = pcl_chamfer_fwd(pred, dtype1, bs1, rs1, nullptr, target, dtype2, bs2, rs2, nullptr, B, N, N, 3, chamfer_mode,
                          (float *)(d + L.dist_x), (int32_t *)(d + L.idx_x), (float *)(d + L.dist_y), (int32_t *)(d + L.idx_y),
                          losses, d + L.ch_ws, pcl_chamfer_workspace_bytes(B, N, N), ss->side);
     if (rc) return rc;
     rc = chamfer_bwd_impl(pred, dtype1, bs1, rs1, nullptr, target, dtype2, bs2, rs2, nullptr, B, N, N, 3, (int32_t *)(d + L.idx_x),
-                          (int32_t *)(d + L.idx_y), nullptr, 1.f, 1.f, grad_pred_chamfer, (float *)(d + L.grad_y), ss->side);
+                          (int32_t *)(d + L.idx_y), nullptr, 1.f, 1.f, grad_pred_chamfer, (float *)(d + L.grad_y), ss->side, true);
     if (rc) return rc;
     PCL_CUDA(cudaEventRecord(ss->join, ss->side));
     PCL_CUDA(cudaStreamWaitEvent(st, ss->join, 0));

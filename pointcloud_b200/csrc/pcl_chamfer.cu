@@ -824,15 +824,17 @@ extern "C" int pcl_chamfer_fwd(const void *x, int x_dtype, int64_t x_bs, int64_t
 int pcl::chamfer_bwd_impl(const void *x, int x_dtype, int64_t x_bs, int64_t x_rs, const int64_t *x_len, const void *y, int y_dtype,
                           int64_t y_bs, int64_t y_rs, const int64_t *y_len, int B, int P1, int P2, int D, const int32_t *idx_x,
                           const int32_t *idx_y, const float *grad_out, float g_imm_x, float g_imm_y, float *grad_x, float *grad_y,
-                          cudaStream_t st) {
+                          cudaStream_t st, bool outputs_are_zero) {
     int rc = check_args(x, x_dtype, y, y_dtype, B, P1, P2, D);
     if (rc) return rc;
     if (B > 0 && ((P1 > 0 && (!grad_x || !idx_x)) || (P2 > 0 && (!grad_y || !idx_y)))) {
         set_error("chamfer_bwd: null argument"); return PCL_E_ARG;
     }
     if (B == 0) return PCL_OK;
-    if (P1 > 0) PCL_CUDA(cudaMemsetAsync(grad_x, 0, (size_t)B * P1 * D * sizeof(float), st));
-    if (P2 > 0) PCL_CUDA(cudaMemsetAsync(grad_y, 0, (size_t)B * P2 * D * sizeof(float), st));
+    if (!outputs_are_zero) {
+        if (P1 > 0) PCL_CUDA(cudaMemsetAsync(grad_x, 0, (size_t)B * P1 * D * sizeof(float), st));
+        if (P2 > 0) PCL_CUDA(cudaMemsetAsync(grad_y, 0, (size_t)B * P2 * D * sizeof(float), st));
+    }
     if (P1 == 0 || P2 == 0) return PCL_OK;
     const Pts xp{x, x_bs, x_rs, x_dtype}, yp{y, y_bs, y_rs, y_dtype};
     const int maxP = P1 > P2 ? P1 : P2;

@@ -59,7 +59,7 @@ __device__ __forceinline__ float3 ld_xyz(const Pts &a, int64_t b, int64_t row) {
 int chamfer_bwd_impl(const void *x, int x_dtype, int64_t x_bs, int64_t x_rs, const int64_t *x_len, const void *y, int y_dtype,
                      int64_t y_bs, int64_t y_rs, const int64_t *y_len, int B, int P1, int P2, int D, const int32_t *idx_x,
                      const int32_t *idx_y, const float *grad_out, float g_imm_x, float g_imm_y, float *grad_x, float *grad_y,
-                     cudaStream_t st);
+                     cudaStream_t st, bool outputs_are_zero = false);  // outputs_are_zero: the caller has zero-filled grad_x / grad_y on `st` already
 
 // pcl_emd_fwd_fused with a say on the worker launch of the ticket path (pcl_emd.cu)
 enum { EMD_WORKERS_AUTO = 0, EMD_WORKERS_NONE_DEDICATED = 1 };
