@@ -432,14 +432,28 @@ def main():
     sum_u, executed = [], []
     for i in range(min(K, 32)):
         p, t, regime = pool[(W + i) % n_sets]
-        m = [ev() for _ in range(5)]
-        m[0].record(); rc = kern.chamfer_fwd(p, t, st); m[1].record(); rc |= kern.chamfer_bwd(p, t, st); m[2].record()
-        rc |= kern.emd_fused(p, t, st); m[3].record(); rc |= kern.emd_bwd(p, t, st); m[4].record()
+        # the short kernels (5-80 us) are timed as the average of REP back-to-back launches on rotating inputs: an event pair around a
+        # single launch would add the event / launch gap (~10 us) to every one of them
+        REP = 8
+        batch = [pool[(W + i * REP + j) % n_sets][:2] for j in range(REP)]
+        m = [ev() for _ in range(6)]
+        rc = 0
+        m[0].record()
+        for pj, tj in batch:
+            rc |= kern.chamfer_fwd(pj, tj, st)
+        m[1].record()
+        for pj, tj in batch:
+            rc |= kern.chamfer_bwd(pj, tj, st)
+        m[2].record()
+        rc |= kern.emd_fused(p, t, st); m[3].record()
+        for pj, tj in batch:
+            rc |= kern.emd_bwd(pj, tj, st)
+        m[4].record()
         torch.cuda.synchronize()
         if rc:
             raise RuntimeError(_lib.lib().pcl_last_error().decode())
-        for name, a, b_ in zip(phases, m[:-1], m[1:]):
-            phases[name].append(a.elapsed_time(b_))
+        for name, a, b_, div in zip(phases, m[:-1], m[1:], (REP, REP, 1, REP)):
+            phases[name].append(a.elapsed_time(b_) / div)
         e_a, e_b = ev(), ev()
         e_a.record(); step.step(p, t); e_b.record()
         torch.cuda.synchronize()
@@ -469,7 +483,7 @@ def main():
     ch_evals = 2.0 * B_PER_GPU * NPTS * NPTS
     ch_ms = statistics.mean(phases["chamfer_fwd"])
     ch_achieved = FLOP_PER_CHAMFER_EVAL * ch_evals / (ch_ms * 1e-3) / 1e12
-    roofline_chamfer = {"kernel": "chamfer_nn3_kernel (one launch incl. the final reduction; + a 4-byte ticket memset)", "bound": "fp32-cuda-core",
+    roofline_chamfer = {"kernel": "chamfer_nn3_kernel (one launch incl. the final reduction; + a 4-byte ticket memset); average of 8 back-to-back launches on rotating inputs", "bound": "fp32-cuda-core",
                         "achieved": ch_achieved, "peak": fp32_peak_tflops, "unit": "TFLOP/s", "frac": ch_achieved / fp32_peak_tflops, "traffic": None,
                         "avg_launch_ms": ch_ms,
                         "algorithmic": f"{FLOP_PER_CHAMFER_EVAL} FLOP x 2*B*N*M directed evaluations = {FLOP_PER_CHAMFER_EVAL * ch_evals:.3e} FLOP per launch",
