@@ -1042,6 +1042,11 @@ int pcl::emd_fwd_fused_impl(const void *xyz1, int dtype1, int64_t bs1, int64_t r
         for (const void *k : kernels) {
             PCL_CUDA(cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, di.max_smem_optin));
             PCL_CUDA(cudaFuncSetAttribute(k, cudaFuncAttributeNonPortableClusterSizeAllowed, 1));
+            // The largest shared-memory carveout (228 KB) instead of the smallest that holds the 183 KB state (196 KB): the 44 KB that are
+            // left let one CTA of another kernel (Chamfer in the composite step: 17 KB, 96 registers) share the SM with an auction CTA.
+            // Late-training steps, where Chamfer on the 20 free SMs ends the step, 376 -> 357 us; early-training steps 1514 -> 1529 us
+            // (the guest competes for issue slots).  Training spends most of its steps in the late regime.  PCL_EMD_NO_CARVEOUT: off.
+            if (!getenv("PCL_EMD_NO_CARVEOUT")) PCL_CUDA(cudaFuncSetAttribute(k, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared));
         }
         attr_dev = dev;
     }
