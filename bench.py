@@ -564,19 +564,18 @@ def main():
         estep.step(sl["p"], sl["t"])                     # the three kernels (+ the all-reduce of the batch sums at N > 1)
         sl["free"].record(cur_stream)
         sl["loss_h"].copy_(estep.stats, non_blocking=True)
+        prefetch(i + 1)                                  # copy of the NEXT step's inputs: issued while this step's kernels run
         cur_stream.synchronize()                         # the caller reads the loss now
         return float(sl["loss_h"][2] / sl["loss_h"][3])
 
     def prefetched(k, w):
         prefetch(0)
         for i in range(w):
-            prefetch(i + 1)
             compute_and_read(i)
         barrier()
         e0, e1 = ev(), ev()
         e0.record()
         for i in range(w, w + k):
-            prefetch(i + 1)                              # copy of the NEXT step's inputs, overlapped with this step's kernels
             compute_and_read(i)
         e1.record()
         barrier()
