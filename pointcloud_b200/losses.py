@@ -406,7 +406,7 @@ class _ChamferEmdStep(torch.autograd.Function):
     def backward(ctx, g_chamfer, g_emd_loss):
         g_ch, g_emd = ctx.saved_tensors
         shape, dtype = ctx.meta
-        g = g_ch * g_chamfer + g_emd * g_emd_loss
+        g = torch.addcmul(g_ch * g_chamfer, g_emd, g_emd_loss)
         if shape[2] != 3:  # more channels than xyz: only xyz receives gradient
             full = torch.zeros(shape, device=g.device, dtype=torch.float32)
             full[:, :, :3] = g
