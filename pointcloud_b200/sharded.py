@@ -93,19 +93,28 @@ class ShardedChamferEmdStep:
     [sum_n chamfer_x, sum_n chamfer_y, sum sqrt(dist), B_r*N].
 
     After `step()` (asynchronous, on torch's current stream):
-      * `stats` (device view, fp32[4]) holds the all-reduced vector; `losses()` turns it into the GLOBAL loss scalars
-        {chamfer = ([0]+[1])/B_global, emd = [2]/[3]} -- what one GPU computes on the gathered batch;
+      * `stats` (device view, fp32[4]) holds the all-reduced vector once `wait()` has been called (it makes the current stream wait
+        for the collective; `losses()` calls it) -- the all-reduce itself is issued asynchronously (NCCL's stream) so that the NEXT
+        step's kernels do not queue behind it: the gradients below never depend on it, only the logged loss does, and the ranks
+        are not forced into lock-step by a 16-byte collective.  Two result buffers alternate; a buffer is re-used only after its
+        collective has completed.  `overlap_collective=False` restores the in-stream all-reduce.
+        `losses()` turns `stats` into the GLOBAL loss scalars {chamfer = ([0]+[1])/B_global, emd = [2]/[3]} -- what one GPU
+        computes on the gathered batch;
       * `grad_chamfer`, `grad_emd` (B_r,N,3) hold d(local mean)/d pred, i.e. world_size * d(global mean)/d(local pred) for
         equal shards: exactly what DistributedDataParallel's gradient averaging expects (same contract as ShardedLoss).
     """
 
-    def __init__(self, batch_local, points, device, eps=0.005, iters=50, chamfer_mode=0, process_group=None):
+    def __init__(self, batch_local, points, device, eps=0.005, iters=50, chamfer_mode=0, process_group=None, overlap_collective=True):
         from . import _lib
         self._lib, self.L = _lib, _lib.lib()
         self.b, self.n, self.eps, self.iters, self.mode, self.group = int(batch_local), int(points), float(eps), int(iters), int(chamfer_mode), process_group
         self.device = device
         f32 = torch.float32
-        self.out = torch.zeros(8, device=device, dtype=f32)   # the `losses` vector of pcl_chamfer_emd_step (include/pcl.h)
+        self._outs = [torch.zeros(8, device=device, dtype=f32) for _ in range(2)]  # the `losses` vector of pcl_chamfer_emd_step (include/pcl.h)
+        self._work = [None, None]
+        self._k = 0
+        self.overlap = bool(overlap_collective)
+        self.out = self._outs[0]
         self.stats = self.out[2:6]
         self.grad_chamfer = torch.empty(self.b, self.n, 3, device=device, dtype=f32)
         self.grad_emd = torch.empty(self.b, self.n, 3, device=device, dtype=f32)
@@ -114,16 +123,33 @@ class ShardedChamferEmdStep:
         self.world = dist.get_world_size(process_group) if (dist.is_available() and dist.is_initialized()) else 1
 
     def step(self, pred, target):
+        k = self._k = self._k ^ 1
+        if self._work[k] is not None:      # the collective that used this buffer two steps ago (long finished; a stream-side wait)
+            self._work[k].wait()
+            self._work[k] = None
+        self.out = self._outs[k]
+        self.stats = self.out[2:6]
         rc = self.L.pcl_chamfer_emd_step(*self._lib.pts_args(pred), *self._lib.pts_args(target), self.b, self.n, self.eps, self.iters, self.mode,
                                          self.out.data_ptr(), self.grad_chamfer.data_ptr(), self.grad_emd.data_ptr(),
                                          self.scratch.data_ptr(), self.scratch_bytes, self._lib.stream_ptr(self.device))
         self._lib.check(rc, "pcl_chamfer_emd_step")
         if self.world > 1:
-            dist.all_reduce(self.stats, op=dist.ReduceOp.SUM, group=self.group)
+            if self.overlap:
+                self._work[k] = dist.all_reduce(self.stats, op=dist.ReduceOp.SUM, group=self.group, async_op=True)
+            else:
+                dist.all_reduce(self.stats, op=dist.ReduceOp.SUM, group=self.group)
+        return self.stats
+
+    def wait(self):
+        """Makes the current stream wait for the all-reduce of the latest step: `stats` is the global vector for whatever is enqueued next."""
+        w = self._work[self._k]
+        if w is not None:
+            w.wait()
+            self._work[self._k] = None
         return self.stats
 
     def losses(self):
         """Global {chamfer, emd} as python floats (synchronises)."""
-        s = self.stats.double().cpu()
+        s = self.wait().double().cpu()
         b_global = float(s[3]) / self.n
         return {"chamfer": float(s[0] + s[1]) / b_global, "emd": float(s[2] / s[3])}
